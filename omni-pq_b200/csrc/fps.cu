@@ -1,0 +1,438 @@
+// Furthest point sampling for sm_100a -- replaces furthest_point_sampling_kernel
+// (reference pointnet2/_ext_src/src/sampling_gpu.cu:74-234, one 512-thread block per cloud that
+// re-streams xyz and a global temp[] array from L2 on every one of the m-1 rounds and reduces
+// through a 9-step __syncthreads tree).
+//
+// FPS is a chain of m-1 dependent arg-max rounds; its compulsory HBM traffic is 12*N + 4*m bytes,
+// so it is latency-bound, not bandwidth-bound.  Design (see DESIGN.md "FPS"):
+//   * one thread-block CLUSTER (1..16 CTAs of 128 threads) per cloud; every point lives in
+//     registers (x, y, z, running min-distance) for the whole kernel -> xyz is read from HBM once
+//     and the reference's temp[] scratch never exists;
+//   * per round: register update -> warp arg-max with redux.sync -> 4 warp candidates through
+//     shared memory (one bar.sync) -> CTA candidate pushed to every CTA of the cluster with
+//     st.async (DSMEM store that completes a transaction on the receiver's mbarrier) -> every warp
+//     reduces the <=16 CTA candidates; the candidate carries the winner's coordinates so the next
+//     round starts without another memory round trip;
+//   * buffers are double-buffered on the round parity, which makes one barrier per level enough.
+//
+// Bit-exactness with the reference (index output):
+//   * d = fmaf(dz,dz, fmaf(dx,dx, dy*dy)) with dx = x_k - x_old (pn2_common.cuh sq3), running
+//     min with fminf, skip of points with (double)|p|^2 <= 1e-3 (sampling_gpu.cu:105-106);
+//   * ties on the max are broken like the reference's tree: thread t = k mod bs scans k ascending
+//     with strict '>' and the tree keeps the lower slot, i.e. the winner minimises
+//     (bitrev(k mod bs), k div bs) -- encoded below as `rank`; bs = pn2_ref_block_size(n);
+//   * if no point is a candidate (all skipped) the reference yields index 0.
+#include <limits.h>
+
+#include <type_traits>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int kFpsThreads = 128;  // resident kernel: 4 warps, one per SM sub-partition
+constexpr int kFpsMaxCluster = 16;
+constexpr int kStreamThreads = 512;  // streaming fallback for clouds beyond register capacity
+constexpr int kFpsMaxPts = 48;       // register-resident points per thread (largest instantiation)
+
+template <int NW>
+struct alignas(16) FpsSmem {
+  uint4 wkey[2][NW];              // per-warp candidate {dist bits, rank, x bits, y bits}
+  uint4 ckey[2][kFpsMaxCluster];  // per-CTA candidates received from the whole cluster
+  float wz[2][NW];
+  float cz[2][kFpsMaxCluster];
+  unsigned long long bar[2];  // one mbarrier per parity buffer
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// DSMEM stores that complete `bytes` on the receiving CTA's mbarrier.
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b,
+                                            uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::
+                   "r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t rbar, uint32_t a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(a), "r"(rbar)
+               : "memory");
+}
+constexpr uint32_t kCandBytes = 20;  // v4.b32 + b32 per CTA candidate
+
+// Tie-break order of the reference tree: smaller rank wins.  rank = (bitrev(k mod bs), k div bs).
+__device__ __forceinline__ uint32_t rank_of(int k, int bs_log2) {
+  const uint32_t low = static_cast<uint32_t>(k) & ((1u << bs_log2) - 1u);
+  return (__brev(low) >> 1) | (static_cast<uint32_t>(k) >> bs_log2);
+}
+__device__ __forceinline__ int index_of_rank(uint32_t r, int bs_log2) {
+  const uint32_t qmask = (1u << (31 - bs_log2)) - 1u;
+  const uint32_t low = __brev((r & ~qmask) << 1);
+  return static_cast<int>(((r & qmask) << bs_log2) | low);
+}
+
+struct Cand {
+  int d;       // float bits of the min-distance (>= 0) or of the -1 "no candidate" sentinel (< 0)
+  uint32_t r;  // tie-break rank
+  float x, y, z;
+};
+
+// Block- and cluster-level arg-max of the per-warp candidates already stored in S.wkey[p]/wz[p].
+// Every thread returns the same winner.
+template <int NW>
+__device__ __forceinline__ Cand reduce_candidates(FpsSmem<NW> &S, int p, int j, int cs, uint32_t my_cta,
+                                                  int warp, int lane) {
+  __syncthreads();
+  Cand c;
+  c.d = INT_MIN;
+  c.r = 0xffffffffu;
+  c.x = c.y = c.z = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const uint4 e = S.wkey[p][w];
+    const bool better = (static_cast<int>(e.x) > c.d) || (static_cast<int>(e.x) == c.d && e.y < c.r);
+    if (better) {
+      c.d = static_cast<int>(e.x);
+      c.r = e.y;
+      c.x = __uint_as_float(e.z);
+      c.y = __uint_as_float(e.w);
+      c.z = S.wz[p][w];
+    }
+  }
+  if (cs > 1) {
+    if (warp == 0 && lane < cs) {
+      const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+      st_async_v4(mapa_u32(smem_u32(&S.ckey[p][my_cta]), lane), rbar, static_cast<uint32_t>(c.d), c.r,
+                  __float_as_uint(c.x), __float_as_uint(c.y));
+      st_async_b32(mapa_u32(smem_u32(&S.cz[p][my_cta]), lane), rbar, __float_as_uint(c.z));
+    }
+    mbar_wait(&S.bar[p], ((j - 1) >> 1) & 1);
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCandBytes);  // re-arm for round j+2
+    int ed = INT_MIN;
+    uint32_t er = 0xffffffffu;
+    if (lane < cs) {
+      const uint4 e = S.ckey[p][lane];
+      ed = static_cast<int>(e.x);
+      er = e.y;
+    }
+    const int gmax = __reduce_max_sync(0xffffffffu, ed);
+    const uint32_t gr = __reduce_min_sync(0xffffffffu, ed == gmax ? er : 0xffffffffu);
+    const int src = __ffs(__ballot_sync(0xffffffffu, ed == gmax && er == gr)) - 1;
+    const uint4 e = S.ckey[p][src];
+    c.d = static_cast<int>(e.x);
+    c.r = e.y;
+    c.x = __uint_as_float(e.z);
+    c.y = __uint_as_float(e.w);
+    c.z = S.cz[p][src];
+  }
+  return c;
+}
+
+template <int NW>
+__device__ __forceinline__ void setup_cluster(FpsSmem<NW> &S, int cs) {
+  if (cs > 1) {
+    if (threadIdx.x == 0) {
+      mbar_init(&S.bar[0], 1);
+      mbar_init(&S.bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_arrive_expect_tx(&S.bar[0], cs * kCandBytes);
+      mbar_arrive_expect_tx(&S.bar[1], cs * kCandBytes);
+    }
+    cluster_sync_all();
+  }
+}
+
+// ---- register-resident kernel ------------------------------------------------------------------
+template <int PTS>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
+                    int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  constexpr int NW = kFpsThreads / 32;
+  using MaskT = typename std::conditional<(PTS > 32), unsigned long long, uint32_t>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FpsSmem<NW> &S = *reinterpret_cast<FpsSmem<NW> *>(smem_raw);
+  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem<NW>));
+  float *sy = sx + PTS * kFpsThreads;
+  float *sz = sy + PTS * kFpsThreads;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
+  const int batch = blockIdx.x / cs;
+  xyz += static_cast<size_t>(batch) * n * 3;
+  idxs += static_cast<size_t>(batch) * m;
+  if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
+  const int T = cs * kFpsThreads;
+  const int g = static_cast<int>(my_cta) * kFpsThreads + tid;
+
+  float px[PTS], py[PTS], pz[PTS], pt[PTS];
+#pragma unroll
+  for (int i = 0; i < PTS; ++i) {
+    const int k = g + i * T;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool valid = false;
+    if (k < n) {
+      x = xyz[k * 3 + 0];
+      y = xyz[k * 3 + 1];
+      z = xyz[k * 3 + 2];
+      valid = !(static_cast<double>(sq3(x, y, z)) <= 1e-3);  // sampling_gpu.cu:105-106
+    }
+    px[i] = x; py[i] = y; pz[i] = z;
+    pt[i] = valid ? 1e10f : -1.0f;  // -1: never a candidate, fminf keeps it at -1
+    sx[i * kFpsThreads + tid] = x;
+    sy[i * kFpsThreads + tid] = y;
+    sz[i * kFpsThreads + tid] = z;
+  }
+  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
+  float x1 = x0, y1 = y0, z1 = z0;
+  if (g == 0) {
+    idxs[0] = 0;
+    if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
+  }
+  setup_cluster(S, cs);
+
+  for (int j = 1; j < m; ++j) {
+    const int p = j & 1;
+    float best = -2.0f;
+#pragma unroll
+    for (int i = 0; i < PTS; ++i) {
+      const float d = dist2(px[i], py[i], pz[i], x1, y1, z1);
+      const float t = fminf(d, pt[i]);
+      pt[i] = t;
+      best = fmaxf(best, t);
+    }
+    const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+    MaskT eqm = 0;  // bit i set <=> this thread's point i attains the warp max
+#pragma unroll
+    for (int i = 0; i < PTS; ++i)
+      if (__float_as_int(pt[i]) == wmax) eqm |= MaskT(1) << i;
+    uint32_t myrank = 0xffffffffu;
+    int ib = 0;
+    while (eqm) {  // one iteration on one lane unless the max is tied
+      const int i = (sizeof(MaskT) == 8 ? __ffsll(static_cast<long long>(eqm)) : __ffs(static_cast<int>(eqm))) - 1;
+      eqm &= eqm - 1;
+      const uint32_t r = rank_of(g + i * T, bs_log2);
+      if (r < myrank) { myrank = r; ib = i; }
+    }
+    const uint32_t wrank = __reduce_min_sync(0xffffffffu, myrank);
+    if (myrank == wrank) {  // ranks are unique -> exactly one lane
+      S.wkey[p][warp] = make_uint4(static_cast<uint32_t>(wmax), wrank, __float_as_uint(sx[ib * kFpsThreads + tid]),
+                                   __float_as_uint(sy[ib * kFpsThreads + tid]));
+      S.wz[p][warp] = sz[ib * kFpsThreads + tid];
+    }
+    const Cand c = reduce_candidates(S, p, j, cs, my_cta, warp, lane);
+    int k = 0;
+    if (c.d < 0) { x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields 0
+    else { k = index_of_rank(c.r, bs_log2); x1 = c.x; y1 = c.y; z1 = c.z; }
+    if (g == 0) {
+      idxs[j] = k;
+      if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
+    }
+  }
+  if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
+}
+
+// ---- streaming fallback (n beyond register capacity): same exchange, points from L2 ---------------
+__global__ void __launch_bounds__(kStreamThreads, 1)
+fps_streaming_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
+                     float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  constexpr int NW = kStreamThreads / 32;
+  __shared__ FpsSmem<NW> S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
+  const int batch = blockIdx.x / cs;
+  xyz += static_cast<size_t>(batch) * n * 3;
+  temp += static_cast<size_t>(batch) * n;
+  idxs += static_cast<size_t>(batch) * m;
+  if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
+  const int T = cs * kStreamThreads;
+  const int g = static_cast<int>(my_cta) * kStreamThreads + tid;
+
+  for (int k = g; k < n; k += T) {
+    const bool valid = !(static_cast<double>(sq3(xyz[k * 3], xyz[k * 3 + 1], xyz[k * 3 + 2])) <= 1e-3);
+    temp[k] = valid ? 1e10f : -1.0f;
+  }
+  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
+  float x1 = x0, y1 = y0, z1 = z0;
+  if (g == 0) {
+    idxs[0] = 0;
+    if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
+  }
+  setup_cluster(S, cs);
+
+  for (int j = 1; j < m; ++j) {
+    const int p = j & 1;
+    float best = -2.0f;
+    uint32_t brank = 0xffffffffu;
+    for (int k = g; k < n; k += T) {
+      const float d = dist2(xyz[k * 3], xyz[k * 3 + 1], xyz[k * 3 + 2], x1, y1, z1);
+      const float t = fminf(d, temp[k]);
+      temp[k] = t;
+      if (t >= best) {
+        const uint32_t r = rank_of(k, bs_log2);
+        if (t > best || r < brank) { best = t; brank = r; }
+      }
+    }
+    const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+    const uint32_t myrank = (__float_as_int(best) == wmax) ? brank : 0xffffffffu;
+    const uint32_t wrank = __reduce_min_sync(0xffffffffu, myrank);
+    const uint32_t win = __ballot_sync(0xffffffffu, __float_as_int(best) == wmax && myrank == wrank);
+    if (lane == __ffs(win) - 1) {
+      float wx = 0.f, wy = 0.f, wzv = 0.f;
+      if (wmax >= 0) {
+        const int k = index_of_rank(wrank, bs_log2);
+        wx = xyz[k * 3]; wy = xyz[k * 3 + 1]; wzv = xyz[k * 3 + 2];
+      }
+      S.wkey[p][warp] = make_uint4(static_cast<uint32_t>(wmax), wrank, __float_as_uint(wx), __float_as_uint(wy));
+      S.wz[p][warp] = wzv;
+    }
+    const Cand c = reduce_candidates(S, p, j, cs, my_cta, warp, lane);
+    int k = 0;
+    if (c.d < 0) { x1 = x0; y1 = y0; z1 = z0; }
+    else { k = index_of_rank(c.r, bs_log2); x1 = c.x; y1 = c.y; z1 = c.z; }
+    if (g == 0) {
+      idxs[j] = k;
+      if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
+    }
+  }
+  if (cs > 1) cluster_sync_all();
+}
+
+// Function attributes are per device: true if `slot` already names the current device, else records it.
+inline bool configured_on(int &slot) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (slot == dev) return true;
+  slot = dev;
+  return false;
+}
+
+template <typename K>
+int launch_cluster(K kernel, int grid, int block, size_t smem, int cs, cudaStream_t stream, void **args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(kernel), args);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pn2_furthest_point_sampling: launch (cluster %d) failed: %s", cs, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return PN2_OK;
+}
+
+template <int PTS>
+int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
+                    cudaStream_t stream) {
+  auto kernel = fps_resident_kernel<PTS>;
+  const size_t smem = sizeof(FpsSmem<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
+  static thread_local int configured_dev = -1;
+  if (!configured_on(configured_dev)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
+  void *args[] = {&n, &m, &cs, &bs_log2, &xyz, &idxs, &new_xyz};
+  return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
+}
+
+constexpr int kPtsOptions[] = {1, 2, 4, 8, 16, 20, 26, 32, 40, 48};
+
+int pick_pts(int need) {
+  for (int v : kPtsOptions)
+    if (v >= need) return v;
+  return 0;
+}
+
+}  // namespace
+}  // namespace pn2
+
+PN2_EXPORT int pn2_fps_resident_capacity(void) { return pn2::kFpsMaxCluster * pn2::kFpsThreads * pn2::kFpsMaxPts; }
+
+PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idxs,
+                                           float *new_xyz, void *stream_) {
+  using namespace pn2;
+  PN2_REQUIRE(b >= 0 && n > 0, "pn2_furthest_point_sampling: need b >= 0 and n > 0 (b=%d n=%d)", b, n);
+  if (b == 0 || m <= 0) return PN2_OK;  // sampling_gpu.cu:78
+  PN2_REQUIRE(xyz && idxs, "pn2_furthest_point_sampling: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int bs = pn2_ref_block_size(n);
+  int bs_log2 = 0;
+  while ((1 << (bs_log2 + 1)) <= bs) ++bs_log2;
+
+  // Cluster size: smallest that keeps <= 16 points per thread; clouds that need more use 16 CTAs
+  // (8 when the batch would not fit the chip in one wave and registers allow).
+  int cs = 1;
+  while (cs < kFpsMaxCluster && (n + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 16) cs *= 2;
+  const int sms = sm_count();
+  while (cs > 1 && b * cs > sms && (n + (cs / 2) * kFpsThreads - 1) / ((cs / 2) * kFpsThreads) <= kFpsMaxPts) cs /= 2;
+  const int need = (n + cs * kFpsThreads - 1) / (cs * kFpsThreads);
+  const int pts = pick_pts(need);
+  if (pts == 0) {
+    PN2_REQUIRE(temp != nullptr, "pn2_furthest_point_sampling: n=%d exceeds the resident capacity %d, temp scratch required",
+                n, pn2_fps_resident_capacity());
+    cs = kFpsMaxCluster;
+    static thread_local int configured_dev = -1;
+    if (!configured_on(configured_dev))
+      cudaFuncSetAttribute(fps_streaming_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    void *args[] = {&n, &m, &cs, &bs_log2, &xyz, &temp, &idxs, &new_xyz};
+    return launch_cluster(fps_streaming_kernel, b * cs, kStreamThreads, 0, cs, stream, args);
+  }
+  switch (pts) {
+#define PN2_FPS_CASE(P) \
+  case P:               \
+    return launch_resident<P>(b, n, m, cs, bs_log2, xyz, idxs, new_xyz, stream);
+    PN2_FPS_CASE(1)
+    PN2_FPS_CASE(2)
+    PN2_FPS_CASE(4)
+    PN2_FPS_CASE(8)
+    PN2_FPS_CASE(16)
+    PN2_FPS_CASE(20)
+    PN2_FPS_CASE(26)
+    PN2_FPS_CASE(32)
+    PN2_FPS_CASE(40)
+    PN2_FPS_CASE(48)
+#undef PN2_FPS_CASE
+  }
+  set_error("pn2_furthest_point_sampling: internal dispatch error (pts=%d)", pts);
+  return PN2_ERR_UNSUPPORTED;
+}

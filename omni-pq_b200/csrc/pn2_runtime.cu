@@ -1,0 +1,53 @@
+// Error reporting and device queries shared by all entry points of libpn2_b200.so.
+#include <math.h>
+#include <stdarg.h>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return PN2_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached > 0 ? cached : 148;
+}
+
+}  // namespace pn2
+
+PN2_EXPORT int pn2_version(void) { return 100; }
+
+PN2_EXPORT const char *pn2_last_error(void) { return pn2::g_err; }
+
+// cuda_utils.h:20-24 of the reference, evaluated the same way (double log ratio, truncation).
+PN2_EXPORT int pn2_ref_block_size(int n) {
+  if (n <= 0) return 1;
+  const int pow_2 = static_cast<int>(log(static_cast<double>(n)) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
