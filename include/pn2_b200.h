@@ -89,6 +89,123 @@ int pn2_three_interpolate(int b, int c, int m, int n, const float *points, const
 int pn2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                const float *weight, float *grad_points, void *stream);
 
+
+/* =====================================================================================================
+ * Fused shared-MLP path (replaces the cuDNN/ATen calls the reference makes through
+ * pytorch_utils.SharedMLP = Conv2d 1x1 (no bias) -> BatchNorm2d -> ReLU, pytorch_utils.py:11-36,67-120,
+ * and F.max_pool2d over nsample, pointnet2_modules.py:254-257, plus their autograd backward).
+ *
+ * Everything works on POSITION-MAJOR activations: a matrix [rows][ld] with one row per position
+ * (position = (cloud, centre, neighbour slot) for set abstraction, (cloud, point) for feature
+ * propagation) and channels contiguous; ld and every channel count are multiples of 4 (zero padded).
+ * A `pn2_rows` describes where the rows of a GEMM operand come from and which element-wise transform
+ * is applied while they are loaded -- that is how grouping, BatchNorm(+ReLU) and the BatchNorm /
+ * max-pool backward are fused into the contraction instead of being separate passes over HBM.
+ * =================================================================================================== */
+#define PN2_ROWS_PLAIN 0   /* v = x[row][c]                                                            */
+#define PN2_ROWS_BNRELU 1  /* v = max(0, x[row][c]*c0[c] + c1[c])            (BN folded to scale/shift) */
+#define PN2_ROWS_GATHER 2  /* v = feat[src(row)][c] for c < feat_cols, then ((xyz[src]-centre)/inv_scale, 0):
+                              QueryAndGroup (pointnet2_utils.py:334-359) without materialising the groups */
+#define PN2_ROWS_DY 3      /* v = c0[c]*dz[row][c] + c1[c] + c2[c]*x[row][c]  (BatchNorm backward, x = pre-BN y) */
+#define PN2_ROWS_DYPOOL 4  /* as DY with dz[row][c] = (arg[g][c] == row % group) ? dz[g][c] : 0, g = row/group
+                              (max-pool backward routed through the saved arg-max slot)                 */
+
+typedef struct pn2_rows {
+  int kind;
+  int rows;  /* positions */
+  int cols;  /* channels this source yields (multiple of 4) */
+  int ld;    /* row stride of x / dz / arg in elements (multiple of 4) */
+  const float *x;
+  const float *c0, *c1, *c2; /* per-channel coefficient vectors, zero padded to cols */
+  const float *dz;
+  const unsigned char *arg;
+  int group;
+  /* PN2_ROWS_GATHER only */
+  const int *idx;       /* [rows] neighbour index inside its cloud (ball query output) */
+  const float *xyz;     /* [B*n_src][3] */
+  const float *centres; /* [B*npoint][3] */
+  int n_src, npoint, nsample;
+  int feat_cols; /* padded feature width, 0 = no features; x = point-major features [B*n_src][ld] */
+  int use_xyz;
+  float inv_scale; /* radius when normalize_xyz, else 1 */
+} pn2_rows;
+
+/* Weights (cout,cin) row-major -> zero padded, optionally column-permuted copies used by the GEMMs:
+ * wt [kp][np] (k-major, for forward) and wp [np][kp] (for dgrad).  `xyz_first` != 0 moves the first three
+ * input channels (the xyz channels QueryAndGroup puts first) behind the `feat_pad` feature channels so
+ * that gathered feature rows stay 16-byte aligned: k' = [features 0..cin-4 | pad | x y z 0]. */
+int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, const float *w,
+                         float *wt, float *wp, void *stream);
+
+/* y[rows][ldy] = A . wt   (A = `a` rows x kp, wt [kp][np]); also writes per-row-tile partial column sums
+ * stats[tiles][2][np] (sum, sum of squares) for BatchNorm; returns the number of row tiles in *tiles.
+ * `stats` may be NULL. */
+int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, float *y, int ldy, float *stats,
+                    int *tiles, void *stream);
+int pn2_mlp_tiles(int rows, int np); /* row tiles pn2_mlp_forward / pn2_mlp_dgrad use for this shape */
+
+/* BatchNorm statistics -> folded scale/shift (+ saved mean / invstd, running-stat update).
+ * training != 0: batch statistics from `stats` (tiles partials) or, if sums != NULL, from the fp64 totals
+ * sums[2][c] with `count` rows (SyncBatchNorm: totals all-reduced by the caller).  training == 0: running
+ * statistics.  gamma/beta may be NULL (affine=False).  momentum < 0 means cumulative average. */
+int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream);
+int pn2_bn_finalize(int training, int tiles, int c, int np, double count, const float *stats, const double *sums,
+                    const float *gamma, const float *beta, float *running_mean, float *running_var,
+                    long long *num_batches_tracked, float momentum, float eps, float *scale, float *shift,
+                    float *mean, float *invstd, void *stream);
+
+/* out_pm[g][c] = max_s relu(y[g*group+s][c]*scale[c]+shift[c]), arg[g][c] = first slot attaining it. */
+int pn2_bn_relu_pool(int groups, int group, int c, int ld, const float *y, const float *scale, const float *shift,
+                     float *out_pm, unsigned char *arg, void *stream);
+
+/* (B,C,N) channel-major <-> point-major rows of `stride` floats per point: to_point_major writes columns
+ * [0,ld) of every row (zeros beyond c), to_channel_major reads columns [0,c). */
+int pn2_to_point_major(int b, int c, int n, int ld, int stride, const float *src, float *dst, void *stream);
+int pn2_to_channel_major(int b, int c, int n, int stride, const float *src, float *dst, void *stream);
+
+/* Backward of pool+ReLU: gz[g][c] = gout_pm[g][c] * (out_pm[g][c] > 0) in place, and partial sums over
+ * groups of gz and gz*y[g*group+arg][c] -> stats[tiles][2][ld]; returns tiles. */
+int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz, const float *out_pm, const unsigned char *arg,
+                      const float *y, float *stats, int *tiles, void *stream);
+int pn2_pool_bwd_tiles(int groups);
+
+/* BatchNorm backward coefficients: dy = ca*dz + cb + cc*y, dgamma, dbeta (training: batch statistics;
+ * eval: ca = gamma*invstd, cb = cc = 0).  Input: partial sums (sum dz, sum dz*y) or fp64 totals. */
+int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, const float *stats, const double *sums,
+                        const float *gamma, const float *mean, const float *invstd, float *ca, float *cb, float *cc,
+                        float *dgamma, float *dbeta, void *stream);
+
+/* dX = dY . wp with dY given by `dy` (kind DY / DYPOOL), wp [kp_out=np of forward][kp].  Modes:
+ *  PN2_DGRAD_MASK: dz_prev = dX * (prev_y*prev_scale+prev_shift > 0) stored to out[rows][ldo], partial
+ *                  sums (dz_prev, dz_prev*prev_y) to stats;
+ *  PN2_DGRAD_STORE: out = dX;
+ *  PN2_DGRAD_SCATTER: dX scatter-added through `gather` (the forward's PN2_ROWS_GATHER source) into
+ *                  dfeat [B*n_src][ldf] and, if dxyz != NULL, into dxyz [B*n_src][3] (both the neighbour's
+ *                  +dX/inv_scale and the centre's -dX/inv_scale via centre_src[B*npoint]). */
+#define PN2_DGRAD_MASK 0
+#define PN2_DGRAD_STORE 1
+#define PN2_DGRAD_SCATTER 2
+int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, float *out, int ldo,
+                  const float *prev_y, int ld_prev, const float *prev_scale, const float *prev_shift, float *stats,
+                  int *tiles, const pn2_rows *gather, float *dfeat, int ldf, float *dxyz, const int *centre_src,
+                  void *stream);
+
+/* dW[cout][cin] = sum_p dY[p][:]^T A[p][:], dY from `dy`, A from `a` (PLAIN / BNRELU / GATHER), written
+ * in the original (cout,cin) layout (undoing the xyz_first permutation).  ws: workspace of
+ * pn2_mlp_wgrad_workspace() floats. */
+long long pn2_mlp_wgrad_workspace(int rows, int np, int kp);
+int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, int cin, int xyz_first, int feat_pad, float *ws,
+                  float *dw, void *stream);
+
+/* Feature propagation front end (three_nn + inverse-distance weights + three_interpolate in one
+ * gather-MAC kernel, pointnet2_modules.py:393-401): writes rows [n][ld] = sum_t w_t * known_pm[idx_t][:]
+ * into out (column offset applied by the caller), plus idx / weight for the backward. */
+int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, const float *unknown, const float *known,
+                       const float *known_pm, float *out, int ldo, int *idx, float *weight, void *stream);
+/* dknown_pm[idx_t][c] += w_t * dout[row][c]  (dknown_pm zero-filled by the caller). */
+int pn2_fp_interpolate_grad(int b, int n, int m, int c, const float *dout, int ldo, const int *idx,
+                            const float *weight, float *dknown_pm, int ld_known, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -227,3 +227,231 @@ def three_interpolate_grad(grad_out, idx, weight, m):
         _check(_interp_grad(b, c, n, int(m), _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(out), _stream()))
     _launched()
     return out
+
+
+# ======================================================================================================
+# Fused shared-MLP path (include/pn2_b200.h, second half).  Thin wrappers: torch allocates, the library
+# computes.  Position-major activations are 2-D tensors [rows, ld] with ld % 4 == 0.
+# ======================================================================================================
+ROWS_PLAIN, ROWS_BNRELU, ROWS_GATHER, ROWS_DY, ROWS_DYPOOL = 0, 1, 2, 3, 4
+DGRAD_MASK, DGRAD_STORE, DGRAD_SCATTER = 0, 1, 2
+
+
+class Rows(ctypes.Structure):
+    """Mirror of `pn2_rows`; `keep` holds the tensors whose pointers it carries."""
+    _fields_ = [("kind", _i), ("rows", _i), ("cols", _i), ("ld", _i),
+                ("x", _vp), ("c0", _vp), ("c1", _vp), ("c2", _vp), ("dz", _vp), ("arg", _vp),
+                ("group", _i),
+                ("idx", _vp), ("xyz", _vp), ("centres", _vp),
+                ("n_src", _i), ("npoint", _i), ("nsample", _i), ("feat_cols", _i), ("use_xyz", _i),
+                ("inv_scale", _f)]
+
+
+def pad4(c):
+    return (int(c) + 3) // 4 * 4
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def rows_plain(x, rows, cols, ld):
+    r = Rows(kind=ROWS_PLAIN, rows=rows, cols=cols, ld=ld, x=_p(x))
+    r.keep = (x,)
+    return r
+
+
+def rows_bnrelu(y, rows, cols, ld, scale, shift):
+    r = Rows(kind=ROWS_BNRELU, rows=rows, cols=cols, ld=ld, x=_p(y), c0=_p(scale), c1=_p(shift))
+    r.keep = (y, scale, shift)
+    return r
+
+
+def rows_gather(feat_pm, ldf, feat_cols, idx, xyz, centres, n_src, npoint, nsample, use_xyz, inv_scale):
+    rows = idx.numel()
+    r = Rows(kind=ROWS_GATHER, rows=rows, cols=feat_cols + (4 if use_xyz else 0), ld=ldf, x=_p(feat_pm),
+             idx=_p(idx), xyz=_p(xyz), centres=_p(centres), n_src=n_src, npoint=npoint, nsample=nsample,
+             feat_cols=feat_cols, use_xyz=int(bool(use_xyz)), inv_scale=float(inv_scale))
+    r.keep = (feat_pm, idx, xyz, centres)
+    return r
+
+
+def rows_dy(y, dz, rows, cols, ld, ca, cb, cc, arg=None, group=1):
+    kind = ROWS_DY if arg is None else ROWS_DYPOOL
+    r = Rows(kind=kind, rows=rows, cols=cols, ld=ld, x=_p(y), c0=_p(ca), c1=_p(cb), c2=_p(cc), dz=_p(dz),
+             arg=_p(arg), group=group)
+    r.keep = (y, dz, ca, cb, cc, arg)
+    return r
+
+
+_rp = ctypes.POINTER(Rows)
+_ip_ = ctypes.POINTER(ctypes.c_int)
+_d = ctypes.c_double
+_prep = _sig("pn2_mlp_prep_weights", _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
+_mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _i, _vp, _ip_, _vp)
+_mlp_tiles = _sig("pn2_mlp_tiles", _i, _i)
+_bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _vp, _vp, _vp)
+_bn_fin = _sig("pn2_bn_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp)
+_pool = _sig("pn2_bn_relu_pool", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
+_to_pm = _sig("pn2_to_point_major", _i, _i, _i, _i, _i, _vp, _vp, _vp)
+_to_cm = _sig("pn2_to_channel_major", _i, _i, _i, _i, _vp, _vp, _vp)
+_pool_prep = _sig("pn2_pool_bwd_prep", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip_, _vp)
+_pool_tiles = _sig("pn2_pool_bwd_tiles", _i)
+_bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
+_wgrad = _sig("pn2_mlp_wgrad", _rp, _rp, _i, _i, _i, _i, _vp, _vp, _vp)
+lib.pn2_mlp_wgrad_workspace.argtypes = [_i, _i, _i]
+lib.pn2_mlp_wgrad_workspace.restype = ctypes.c_longlong
+_fp_interp = _sig("pn2_fp_interpolate", _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp)
+_fp_interp_grad = _sig("pn2_fp_interpolate_grad", _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp)
+
+
+def _f32(dev, *shape, zero=False):
+    return (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=dev)
+
+
+def mlp_prep_weights(w2d, xyz_first, feat_pad, kp, np_):
+    """(cout,cin) weights -> (wt [kp,np], wp [np,kp]) padded / permuted copies."""
+    cout, cin = w2d.shape
+    wt, wp = _f32(w2d.device, kp, np_), _f32(w2d.device, np_, kp)
+    _check(_prep(cout, cin, int(xyz_first), feat_pad, kp, np_, _ptr(w2d), _ptr(wt), _ptr(wp), _stream()))
+    _launched()
+    return wt, wp
+
+
+def mlp_forward(rows, kp, np_, wt, want_stats=True):
+    dev = wt.device
+    y = _f32(dev, rows.rows, np_)
+    tiles = _mlp_tiles(rows.rows, np_)
+    stats = _f32(dev, max(tiles, 1), 2, np_) if want_stats else None
+    t = ctypes.c_int(0)
+    _check(_mlp_fwd(ctypes.byref(rows), kp, np_, _ptr(wt), _ptr(y), np_, _p(stats), ctypes.byref(t), _stream()))
+    _launched()
+    return y, stats, tiles
+
+
+def bn_reduce_stats(stats, tiles, c, np_):
+    sums = torch.empty(2, c, dtype=torch.float64, device=stats.device)
+    _check(_bn_reduce(tiles, c, np_, _ptr(stats), _ptr(sums), _stream()))
+    _launched()
+    return sums
+
+
+def bn_finalize(training, tiles, c, np_, count, stats, sums, bn):
+    """-> (scale, shift, mean, invstd), each [np_].  Updates bn's running statistics when training."""
+    dev = bn.running_mean.device if bn.running_mean is not None else (stats if stats is not None else sums).device
+    out = _f32(dev, 4, np_)
+    track = training and bn.track_running_stats and bn.running_mean is not None
+    mom = -1.0 if bn.momentum is None else float(bn.momentum)
+    _check(_bn_fin(int(training), tiles, c, np_, float(count), _p(stats), _p(sums), _p(bn.weight), _p(bn.bias),
+                   _p(bn.running_mean) if (track or not training) else None,
+                   _p(bn.running_var) if (track or not training) else None,
+                   _p(bn.num_batches_tracked) if track else None, mom, float(bn.eps),
+                   _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()))
+    _launched(2 if track and bn.num_batches_tracked is not None else 1)
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_relu_pool(y, groups, group, c, ld, scale, shift, want_arg=True):
+    out_pm = _f32(y.device, groups, ld)
+    arg = torch.empty(groups, ld, dtype=torch.uint8, device=y.device) if want_arg else None
+    _check(_pool(groups, group, c, ld, _ptr(y), _ptr(scale), _ptr(shift), _ptr(out_pm), _p(arg), _stream()))
+    _launched()
+    return out_pm, arg
+
+
+def to_point_major(src, ld=None, out=None, col0=0):
+    """(B,C,N) -> [B*N, ld] (or into columns col0.. of `out`, whose row stride is out.shape[1])."""
+    b, c, n = src.shape
+    ld = pad4(c) if ld is None else ld
+    if out is None:
+        out = _f32(src.device, b * n, ld)
+    stride = out.shape[1]
+    _check(_to_pm(b, c, n, ld, stride, _ptr(src), _vp(out.data_ptr() + 4 * col0), _stream()))
+    _launched()
+    return out
+
+
+def to_channel_major(src_pm, b, c, n, col0=0):
+    """[B*N, stride] (columns col0..col0+c) -> (B,C,N)."""
+    out = _f32(src_pm.device, b, c, n)
+    _check(_to_cm(b, c, n, src_pm.shape[1], _vp(src_pm.data_ptr() + 4 * col0), _ptr(out), _stream()))
+    _launched()
+    return out
+
+
+def pool_bwd_prep(gz, out_pm, arg, y, groups, group, c, ld):
+    tiles = _pool_tiles(groups)
+    stats = _f32(gz.device, max(tiles, 1), 2, ld)
+    t = ctypes.c_int(0)
+    _check(_pool_prep(groups, group, c, ld, _ptr(gz), _ptr(out_pm), _p(arg), _ptr(y), _ptr(stats), ctypes.byref(t),
+                      _stream()))
+    _launched()
+    return stats, tiles
+
+
+def bn_bwd_finalize(training, tiles, c, np_, count, stats, sums, gamma, mean, invstd):
+    """-> (ca, cb, cc [np_] coefficient vectors, dgamma [c], dbeta [c])."""
+    dev = mean.device
+    co = _f32(dev, 3, np_)
+    dg = _f32(dev, 2, c)
+    _check(_bn_bwd(int(training), tiles, c, np_, float(count), _p(stats), _p(sums), _p(gamma), _ptr(mean), _ptr(invstd),
+                   _ptr(co[0]), _ptr(co[1]), _ptr(co[2]), _ptr(dg[0]), _ptr(dg[1]), _stream()))
+    _launched()
+    return co[0], co[1], co[2], dg[0], dg[1]
+
+
+def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift):
+    """dz_prev [rows, ncols] and its BatchNorm-backward partial sums."""
+    dev = wp.device
+    out = _f32(dev, dy.rows, ncols)
+    tiles = _mlp_tiles(dy.rows, ncols)
+    stats = _f32(dev, max(tiles, 1), 2, ncols)
+    t = ctypes.c_int(0)
+    _check(_dgrad(DGRAD_MASK, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, _ptr(prev_y),
+                  prev_y.shape[1], _ptr(prev_scale), _ptr(prev_shift), _ptr(stats), ctypes.byref(t), None, None, 0,
+                  None, None, _stream()))
+    _launched()
+    return out, stats, tiles
+
+
+def mlp_dgrad_store(dy, ncols, wp):
+    out = _f32(wp.device, dy.rows, ncols)
+    _check(_dgrad(DGRAD_STORE, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, None, 0, None, None,
+                  None, None, None, None, 0, None, None, _stream()))
+    _launched()
+    return out
+
+
+def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src):
+    _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], None, 0, None, 0, None, None, None,
+                  None, ctypes.byref(gather), _p(dfeat), dfeat.shape[1] if dfeat is not None else 0, _p(dxyz),
+                  _p(centre_src), _stream()))
+    _launched()
+
+
+def mlp_wgrad(dy, a, cout, cin, xyz_first, feat_pad, dev):
+    ws = _f32(dev, max(1, lib.pn2_mlp_wgrad_workspace(dy.rows, dy.cols, a.cols)))
+    dw = _f32(dev, cout, cin)
+    _check(_wgrad(ctypes.byref(dy), ctypes.byref(a), cout, cin, int(xyz_first), feat_pad, _ptr(ws), _ptr(dw), _stream()))
+    _launched(2)
+    return dw
+
+
+def fp_interpolate(unknown, known, known_pm, c, out, ldo):
+    """three_nn + weights + three_interpolate into columns [0,c) of `out` [B*n, ldo]; -> (idx, weight)."""
+    b, n, _ = unknown.shape
+    m = known.shape[1]
+    idx = torch.empty(b, n, 3, dtype=torch.int32, device=unknown.device)
+    w = _f32(unknown.device, b, n, 3)
+    _check(_fp_interp(b, n, m, c, known_pm.shape[1], _ptr(unknown), _ptr(known), _ptr(known_pm), _ptr(out), ldo,
+                      _ptr(idx), _ptr(w), _stream()))
+    _launched()
+    return idx, w
+
+
+def fp_interpolate_grad(dout, ldo, idx, weight, b, n, m, c, ld_known):
+    dk = _f32(dout.device, b * m, ld_known, zero=True)
+    _check(_fp_interp_grad(b, n, m, c, _ptr(dout), ldo, _ptr(idx), _ptr(weight), _ptr(dk), ld_known, _stream()))
+    _launched()
+    return dk

@@ -1,0 +1,430 @@
+// Element-wise / reduction companions of the shared-MLP GEMMs (mlp_gemm.cu): layout changes between the
+// reference's channel-major API tensors (B,C,N) and the position-major activations the GEMMs use,
+// BatchNorm statistics -> folded scale/shift (forward) and -> backward coefficients, the fused
+// BatchNorm+ReLU+max-pool over nsample (reference F.max_pool2d, pointnet2_modules.py:254-257) with its
+// backward preparation, and the feature-propagation front end (three_nn + inverse-distance weights +
+// three_interpolate, pointnet2_modules.py:393-401) as one gather-MAC kernel.
+// All of these are HBM-bound streaming kernels: 128-bit accesses along the channel dimension, grids
+// sized from the problem so a single cloud still covers the chip.
+#include <math_constants.h>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// ---- (B,C,N) <-> (B,N,ld) ----------------------------------------------------------------------------
+// 32x32 tiles through shared memory, coalesced on both sides; columns c..ld-1 of the point-major side
+// are written as zeros.
+__global__ void __launch_bounds__(256)
+to_point_major_kernel(int c, int n, int ld, int stride, const float *__restrict__ src, float *__restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  src += static_cast<size_t>(b) * c * n;
+  dst += static_cast<size_t>(b) * n * stride;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int cc = c0 + r, nn = n0 + tx;
+    tile[r][tx] = (cc < c && nn < n) ? src[static_cast<size_t>(cc) * n + nn] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int nn = n0 + r, cc = c0 + tx;
+    if (nn < n && cc < ld) dst[static_cast<size_t>(nn) * stride + cc] = tile[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+to_channel_major_kernel(int c, int n, int stride, const float *__restrict__ src, float *__restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  src += static_cast<size_t>(b) * n * stride;
+  dst += static_cast<size_t>(b) * c * n;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int nn = n0 + r, cc = c0 + tx;
+    tile[r][tx] = (nn < n && cc < c) ? src[static_cast<size_t>(nn) * stride + cc] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int cc = c0 + r, nn = n0 + tx;
+    if (cc < c && nn < n) dst[static_cast<size_t>(cc) * n + nn] = tile[tx][r];
+  }
+}
+
+// ---- BatchNorm statistics ---------------------------------------------------------------------------
+// stats[tiles][2][np] fp32 partials -> fp64 totals (fixed order => deterministic)
+__device__ __forceinline__ void total_of(const float *stats, int tiles, int np, int ch, double &s1, double &s2) {
+  s1 = 0.0; s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    s1 += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 0) * np + ch]);
+    s2 += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 1) * np + ch]);
+  }
+}
+
+__global__ void bn_reduce_stats_kernel(int tiles, int c, int np, const float *__restrict__ stats,
+                                       double *__restrict__ sums) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s1, s2;
+  total_of(stats, tiles, np, ch, s1, s2);
+  sums[ch] = s1;
+  sums[c + ch] = s2;
+}
+
+__global__ void bn_finalize_kernel(int training, int tiles, int c, int np, double count,
+                                   const float *__restrict__ stats, const double *__restrict__ sums,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var,
+                                   long long *__restrict__ nbt, float momentum, float eps, float *__restrict__ scale,
+                                   float *__restrict__ shift, float *__restrict__ mean_out,
+                                   float *__restrict__ invstd_out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= np) return;
+  if (ch >= c) {  // zero padding: padded channels stay exactly 0 through BN+ReLU
+    scale[ch] = 0.f; shift[ch] = 0.f; mean_out[ch] = 0.f; invstd_out[ch] = 0.f;
+    return;
+  }
+  float mean, invstd;
+  if (training) {
+    double s1, s2;
+    if (sums) { s1 = sums[ch]; s2 = sums[c + ch]; }
+    else total_of(stats, tiles, np, ch, s1, s2);
+    const double mu = s1 / count;
+    double var = s2 / count - mu * mu;  // biased variance (what BatchNorm normalises with)
+    if (var < 0.0) var = 0.0;
+    mean = static_cast<float>(mu);
+    invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (running_mean && running_var) {
+      // momentum < 0: cumulative moving average with factor 1/num_batches_tracked (after increment)
+      const double f = momentum >= 0.f ? static_cast<double>(momentum)
+                                       : 1.0 / static_cast<double>((nbt ? *nbt : 0) + 1);
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[ch] = static_cast<float>((1.0 - f) * running_mean[ch] + f * mu);
+      running_var[ch] = static_cast<float>((1.0 - f) * running_var[ch] + f * unbiased);
+    }
+  } else {
+    mean = running_mean[ch];
+    invstd = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[ch]) + static_cast<double>(eps)));
+  }
+  const float gmm = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+  const float sc = gmm * invstd;
+  scale[ch] = sc;
+  shift[ch] = fmaf(-mean, sc, bt);
+  mean_out[ch] = mean;
+  invstd_out[ch] = invstd;
+}
+
+__global__ void bn_bump_counter_kernel(long long *nbt) { *nbt += 1; }
+
+__global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, double count,
+                                       const float *__restrict__ stats, const double *__restrict__ sums,
+                                       const float *__restrict__ gamma, const float *__restrict__ mean,
+                                       const float *__restrict__ invstd, float *__restrict__ ca,
+                                       float *__restrict__ cb, float *__restrict__ cc, float *__restrict__ dgamma,
+                                       float *__restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= np) return;
+  if (ch >= c) {
+    ca[ch] = 0.f; cb[ch] = 0.f; cc[ch] = 0.f;
+    return;
+  }
+  double s_dz, s_dzy;
+  if (sums) { s_dz = sums[ch]; s_dzy = sums[c + ch]; }
+  else total_of(stats, tiles, np, ch, s_dz, s_dzy);
+  const double mu = mean[ch], r = invstd[ch], gmm = gamma ? gamma[ch] : 1.0;
+  const double s_dzn = r * (s_dzy - mu * s_dz);  // sum dz * normalised y
+  if (dgamma) dgamma[ch] = static_cast<float>(s_dzn);
+  if (dbeta) dbeta[ch] = static_cast<float>(s_dz);
+  const double s = gmm * r;
+  if (training) {
+    const double m1 = s_dz / count, m2 = s_dzn / count;
+    const double kc = -s * m2 * r;
+    ca[ch] = static_cast<float>(s);
+    cc[ch] = static_cast<float>(kc);
+    cb[ch] = static_cast<float>(-s * m1 - kc * mu);
+  } else {
+    ca[ch] = static_cast<float>(s);
+    cb[ch] = 0.f;
+    cc[ch] = 0.f;
+  }
+}
+
+// ---- BN + ReLU + max over the nsample rows of a group -----------------------------------------------
+// one thread per (group, 4 channels); consecutive threads -> consecutive channels (coalesced 128-bit rows)
+__global__ void __launch_bounds__(256)
+bn_relu_pool_kernel(int groups, int group, int ld, const float *__restrict__ y, const float *__restrict__ scale,
+                    const float *__restrict__ shift, float *__restrict__ out_pm, unsigned char *__restrict__ arg) {
+  const int q = ld / 4;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(groups) * q) return;
+  const int g = static_cast<int>(t / q), c4 = static_cast<int>(t % q) * 4;
+  const float4 sc = ldg4(scale + c4), sh = ldg4(shift + c4);
+  const float *row = y + static_cast<size_t>(g) * group * ld + c4;
+  float4 best = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  uchar4 bi = make_uchar4(0, 0, 0, 0);
+  for (int s = 0; s < group; ++s) {
+    const float4 v = ldg4(row + static_cast<size_t>(s) * ld);
+    const float a = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), b = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    const float c = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), d = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    if (a > best.x) { best.x = a; bi.x = s; }
+    if (b > best.y) { best.y = b; bi.y = s; }
+    if (c > best.z) { best.z = c; bi.z = s; }
+    if (d > best.w) { best.w = d; bi.w = s; }
+  }
+  *reinterpret_cast<float4 *>(out_pm + static_cast<size_t>(g) * ld + c4) = best;
+  if (arg) *reinterpret_cast<uchar4 *>(arg + static_cast<size_t>(g) * ld + c4) = bi;
+}
+
+// gz = gout * (out > 0) in place; partial sums over a strip of groups of gz and gz * y[arg]
+constexpr int kPrepGroups = 32;  // groups per CTA strip
+
+__global__ void __launch_bounds__(128)
+pool_bwd_prep_kernel(int groups, int group, int ld, float *__restrict__ gz, const float *__restrict__ out_pm,
+                     const unsigned char *__restrict__ arg, const float *__restrict__ y,
+                     float *__restrict__ stats) {
+  const int g0 = blockIdx.x * kPrepGroups;
+  for (int c4 = threadIdx.x * 4; c4 < ld; c4 += blockDim.x * 4) {
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    for (int g = g0; g < min(groups, g0 + kPrepGroups); ++g) {
+      const size_t o = static_cast<size_t>(g) * ld + c4;
+      float4 v = *reinterpret_cast<const float4 *>(gz + o);
+      const float4 z = ldg4(out_pm + o);
+      v.x = z.x > 0.f ? v.x : 0.f; v.y = z.y > 0.f ? v.y : 0.f;
+      v.z = z.z > 0.f ? v.z : 0.f; v.w = z.w > 0.f ? v.w : 0.f;
+      *reinterpret_cast<float4 *>(gz + o) = v;
+      uchar4 a = make_uchar4(0, 0, 0, 0);
+      if (arg) a = __ldg(reinterpret_cast<const uchar4 *>(arg + o));
+      const float *yr = y + static_cast<size_t>(g) * group * ld + c4;
+      const float y0 = __ldg(yr + static_cast<size_t>(a.x) * ld + 0), y1 = __ldg(yr + static_cast<size_t>(a.y) * ld + 1);
+      const float y2 = __ldg(yr + static_cast<size_t>(a.z) * ld + 2), y3 = __ldg(yr + static_cast<size_t>(a.w) * ld + 3);
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x = fmaf(v.x, y0, s2.x); s2.y = fmaf(v.y, y1, s2.y); s2.z = fmaf(v.z, y2, s2.z); s2.w = fmaf(v.w, y3, s2.w);
+    }
+    float *dst = stats + static_cast<size_t>(blockIdx.x) * 2 * ld + c4;
+    *reinterpret_cast<float4 *>(dst) = s1;
+    *reinterpret_cast<float4 *>(dst + ld) = s2;
+  }
+}
+
+// ---- feature propagation front end --------------------------------------------------------------------
+// Phase 1 (per unknown point): 3-NN exactly like three_nn_kernel (interpolate_gpu.cu:14-64) + weights
+// w_t = (1/(sqrt(d2_t)+1e-8)) / sum (pointnet2_modules.py:395-397).  Phase 2: the warp that owns the point
+// streams the three known rows (point-major, 128-bit) and writes the blended row.
+constexpr int kFpThreads = 128;
+constexpr int kFpTile = 1024;
+
+__global__ void __launch_bounds__(kFpThreads)
+fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restrict__ unknown,
+                      const float *__restrict__ known, const float *__restrict__ known_pm, float *__restrict__ out,
+                      int ldo, int *__restrict__ idx_out, float *__restrict__ w_out) {
+  __shared__ float tile[kFpTile * 3];
+  __shared__ int s_idx[kFpThreads][3];
+  __shared__ float s_w[kFpThreads][3];
+  const int b = blockIdx.y;
+  unknown += static_cast<size_t>(b) * n * 3;
+  known += static_cast<size_t>(b) * m * 3;
+  const int j = blockIdx.x * kFpThreads + threadIdx.x;
+  const bool live = j < n;
+  const int jj = live ? j : n - 1;
+  const float ux = unknown[jj * 3 + 0], uy = unknown[jj * 3 + 1], uz = unknown[jj * 3 + 2];
+  float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int base = 0; base < m; base += kFpTile) {
+    const int tn = min(kFpTile, m - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += kFpThreads) tile[i] = known[base * 3 + i];
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < tn; ++k) {
+      const float d = dist2(ux, uy, uz, tile[k * 3 + 0], tile[k * 3 + 1], tile[k * 3 + 2]);
+      if (d < b3) {
+        const int kk = base + k;
+        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk; }
+        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = kk; }
+        else { b3 = d; i3 = kk; }
+      }
+    }
+  }
+  // dist = sqrt(dist2); recip = 1/(dist + 1e-8); w = recip / sum(recip)   (left-to-right sum like torch.sum)
+  const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+  const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+  const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+  const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+  const float w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm), w3 = __fdiv_rn(r3, norm);
+  s_idx[threadIdx.x][0] = i1; s_idx[threadIdx.x][1] = i2; s_idx[threadIdx.x][2] = i3;
+  s_w[threadIdx.x][0] = w1; s_w[threadIdx.x][1] = w2; s_w[threadIdx.x][2] = w3;
+  if (live) {
+    int *io = idx_out + (static_cast<size_t>(b) * n + j) * 3;
+    float *wo = w_out + (static_cast<size_t>(b) * n + j) * 3;
+    io[0] = i1; io[1] = i2; io[2] = i3;
+    wo[0] = w1; wo[1] = w2; wo[2] = w3;
+  }
+  __syncthreads();
+  // phase 2: each warp blends the rows of its 32 points, one point at a time, lanes across channels
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float *kp = known_pm + static_cast<size_t>(b) * m * ld_known;
+  for (int p = 0; p < 32; ++p) {
+    const int t = warp * 32 + p, jp = blockIdx.x * kFpThreads + t;
+    if (jp >= n) break;
+    const float *ra = kp + static_cast<size_t>(s_idx[t][0]) * ld_known;
+    const float *rb = kp + static_cast<size_t>(s_idx[t][1]) * ld_known;
+    const float *rc = kp + static_cast<size_t>(s_idx[t][2]) * ld_known;
+    const float wa = s_w[t][0], wb = s_w[t][1], wc = s_w[t][2];
+    float *o = out + (static_cast<size_t>(b) * n + jp) * ldo;
+    for (int q = lane; q < c4n; q += 32) {
+      const float4 a = ldg4(ra + q * 4), bb = ldg4(rb + q * 4), cc = ldg4(rc + q * 4);
+      float4 r;  // interpolate_gpu.cu:103-104 contraction: p2*w2, then fma p1*w1, then fma p3*w3
+      r.x = __fmaf_rn(cc.x, wc, __fmaf_rn(a.x, wa, __fmul_rn(bb.x, wb)));
+      r.y = __fmaf_rn(cc.y, wc, __fmaf_rn(a.y, wa, __fmul_rn(bb.y, wb)));
+      r.z = __fmaf_rn(cc.z, wc, __fmaf_rn(a.z, wa, __fmul_rn(bb.z, wb)));
+      r.w = __fmaf_rn(cc.w, wc, __fmaf_rn(a.w, wa, __fmul_rn(bb.w, wb)));
+      *reinterpret_cast<float4 *>(o + q * 4) = r;
+    }
+  }
+}
+
+// dknown_pm[idx_t][c] += w_t * dout[row][c]; one warp per unknown point, lanes across channels
+__global__ void __launch_bounds__(256)
+fp_interpolate_grad_kernel(int n, int m, int c4n, const float *__restrict__ dout, int ldo,
+                           const int *__restrict__ idx, const float *__restrict__ weight,
+                           float *__restrict__ dknown_pm, int ld_known) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const size_t row = static_cast<size_t>(b) * n + j;
+  const int *ix = idx + row * 3;
+  const float *w = weight + row * 3;
+  float *base = dknown_pm + static_cast<size_t>(b) * m * ld_known;
+  const float *g = dout + row * ldo;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    float *dst = base + static_cast<size_t>(ix[t]) * ld_known;
+    const float wt = w[t];
+    for (int q = lane; q < c4n; q += 32) {
+      const float4 v = ldg4(g + q * 4);
+      atomicAdd(dst + q * 4 + 0, __fmul_rn(v.x, wt));
+      atomicAdd(dst + q * 4 + 1, __fmul_rn(v.y, wt));
+      atomicAdd(dst + q * 4 + 2, __fmul_rn(v.z, wt));
+      atomicAdd(dst + q * 4 + 3, __fmul_rn(v.w, wt));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pn2
+
+using namespace pn2;
+
+static int transpose_launch(bool to_pm, int b, int c, int n, int ld, int stride, const float *src, float *dst,
+                            void *stream, const char *what) {
+  PN2_REQUIRE(b >= 0 && c >= 0 && n >= 0 && ld >= c && stride >= ld, "%s: bad extents b=%d c=%d n=%d ld=%d stride=%d", what, b,
+              c, n, ld, stride);
+  const int cc = to_pm ? ld : c;
+  if (b == 0 || n == 0 || cc == 0) return PN2_OK;
+  PN2_REQUIRE(src && dst && b <= 65535, "%s: null pointer or batch too large", what);
+  dim3 grid((n + 31) / 32, (cc + 31) / 32, b);
+  PN2_REQUIRE(grid.y <= 65535, "%s: too many channels", what);
+  if (to_pm)
+    to_point_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c, n, ld, stride, src, dst);
+  else
+    to_channel_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c, n, stride, src, dst);
+  return check_launch(what);
+}
+
+PN2_EXPORT int pn2_to_point_major(int b, int c, int n, int ld, int stride, const float *src, float *dst, void *stream) {
+  return transpose_launch(true, b, c, n, ld, stride, src, dst, stream, "pn2_to_point_major");
+}
+PN2_EXPORT int pn2_to_channel_major(int b, int c, int n, int stride, const float *src, float *dst, void *stream) {
+  return transpose_launch(false, b, c, n, c, stride, src, dst, stream, "pn2_to_channel_major");
+}
+
+PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream) {
+  PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
+  bn_reduce_stats_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(tiles, c, np, stats, sums);
+  return check_launch("pn2_bn_reduce_stats");
+}
+
+PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double count, const float *stats,
+                               const double *sums, const float *gamma, const float *beta, float *running_mean,
+                               float *running_var, long long *num_batches_tracked, float momentum, float eps,
+                               float *scale, float *shift, float *mean, float *invstd, void *stream_) {
+  PN2_REQUIRE(c > 0 && np >= c && (np % 4) == 0 && scale && shift && mean && invstd, "pn2_bn_finalize: bad arguments");
+  PN2_REQUIRE(training ? ((stats || sums) && count > 0.0) : (running_mean && running_var),
+              "pn2_bn_finalize: %s", training ? "training needs statistics and a positive count" : "eval needs running statistics");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  bn_finalize_kernel<<<(np + 127) / 128, 128, 0, s>>>(training, tiles, c, np, count, stats, sums, gamma, beta,
+                                                       running_mean, running_var, num_batches_tracked, momentum, eps,
+                                                       scale, shift, mean, invstd);
+  if (int rc = check_launch("pn2_bn_finalize")) return rc;
+  if (training && num_batches_tracked && running_mean) {
+    bn_bump_counter_kernel<<<1, 1, 0, s>>>(num_batches_tracked);
+    return check_launch("pn2_bn_finalize(counter)");
+  }
+  return PN2_OK;
+}
+
+PN2_EXPORT int pn2_bn_relu_pool(int groups, int group, int c, int ld, const float *y, const float *scale,
+                                const float *shift, float *out_pm, unsigned char *arg, void *stream) {
+  PN2_REQUIRE(groups >= 0 && group > 0 && group <= 256 && c > 0 && ld >= c && (ld % 4) == 0, "pn2_bn_relu_pool: bad extents groups=%d group=%d c=%d ld=%d",
+              groups, group, c, ld);
+  if (groups == 0) return PN2_OK;
+  PN2_REQUIRE(y && scale && shift && out_pm, "pn2_bn_relu_pool: null pointer");
+  const long long total = static_cast<long long>(groups) * (ld / 4);
+  bn_relu_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      groups, group, ld, y, scale, shift, out_pm, arg);
+  return check_launch("pn2_bn_relu_pool");
+}
+
+PN2_EXPORT int pn2_pool_bwd_tiles(int groups) { return (groups + kPrepGroups - 1) / kPrepGroups; }
+
+PN2_EXPORT int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz, const float *out_pm,
+                                 const unsigned char *arg, const float *y, float *stats, int *tiles, void *stream) {
+  PN2_REQUIRE(groups >= 0 && group > 0 && c > 0 && ld >= c && (ld % 4) == 0, "pn2_pool_bwd_prep: bad extents");
+  if (tiles) *tiles = pn2_pool_bwd_tiles(groups);
+  if (groups == 0) return PN2_OK;
+  PN2_REQUIRE(gz && out_pm && y && stats && (arg || group == 1), "pn2_pool_bwd_prep: null pointer");
+  pool_bwd_prep_kernel<<<pn2_pool_bwd_tiles(groups), 128, 0, static_cast<cudaStream_t>(stream)>>>(groups, group, ld, gz,
+                                                                                                out_pm, arg, y, stats);
+  return check_launch("pn2_pool_bwd_prep");
+}
+
+PN2_EXPORT int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, const float *stats,
+                                   const double *sums, const float *gamma, const float *mean, const float *invstd,
+                                   float *ca, float *cb, float *cc, float *dgamma, float *dbeta, void *stream) {
+  PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && count > 0.0,
+              "pn2_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(np + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      training, tiles, c, np, count, stats, sums, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
+  return check_launch("pn2_bn_bwd_finalize");
+}
+
+PN2_EXPORT int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, const float *unknown, const float *known,
+                                  const float *known_pm, float *out, int ldo, int *idx, float *weight, void *stream) {
+  PN2_REQUIRE(b >= 0 && n >= 0 && m > 0 && c > 0 && (c % 4) == 0 && ld_known >= c && ldo >= c && (ld_known % 4) == 0 && (ldo % 4) == 0,
+              "pn2_fp_interpolate: bad extents b=%d n=%d m=%d c=%d ld_known=%d ldo=%d", b, n, m, c, ld_known, ldo);
+  if (b == 0 || n == 0) return PN2_OK;
+  PN2_REQUIRE(unknown && known && known_pm && out && idx && weight && b <= 65535, "pn2_fp_interpolate: null pointer");
+  dim3 grid((n + kFpThreads - 1) / kFpThreads, b);
+  fp_interpolate_kernel<<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, ld_known, unknown, known,
+                                                                                  known_pm, out, ldo, idx, weight);
+  return check_launch("pn2_fp_interpolate");
+}
+
+PN2_EXPORT int pn2_fp_interpolate_grad(int b, int n, int m, int c, const float *dout, int ldo, const int *idx,
+                                       const float *weight, float *dknown_pm, int ld_known, void *stream) {
+  PN2_REQUIRE(b >= 0 && n >= 0 && m > 0 && c > 0 && (c % 4) == 0 && ld_known >= c && ldo >= c, "pn2_fp_interpolate_grad: bad extents");
+  if (b == 0 || n == 0) return PN2_OK;
+  PN2_REQUIRE(dout && idx && weight && dknown_pm && b <= 65535, "pn2_fp_interpolate_grad: null pointer");
+  dim3 grid((n + 7) / 8, b);
+  fp_interpolate_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, dout, ldo, idx, weight,
+                                                                                dknown_pm, ld_known);
+  return check_launch("pn2_fp_interpolate_grad");
+}

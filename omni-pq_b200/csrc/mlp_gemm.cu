@@ -1,0 +1,520 @@
+// Shared-MLP contractions for sm_100a: forward, data-gradient and weight-gradient GEMMs of the 1x1
+// convolutions in pytorch_utils.SharedMLP (reference pointnet2/pytorch_utils.py:11-36,67-120; the
+// reference runs them as cuDNN convolutions with separate BatchNorm / ReLU / max_pool2d / grouping
+// kernels around them, pointnet2_modules.py:233-267, pointnet2_utils.py:334-359).
+//
+// One templated fp32 kernel, C[M x N] = sum_k A(m,k) * B(k,n), whose operands are *row sources*
+// (include/pn2_b200.h `pn2_rows`): the element-wise work that surrounds the contraction in the
+// reference -- neighbourhood grouping with centre subtraction, BatchNorm+ReLU of the previous layer,
+// the BatchNorm / ReLU / max-pool backward -- is applied in registers while a tile is staged into
+// shared memory, and the epilogue produces BatchNorm partial statistics (or scatter-adds into the
+// gathered inputs), so none of those intermediates makes its own trip through HBM.
+//
+// Arithmetic: plain fp32 FFMA with a fixed k-ascending accumulation order (deterministic, and the
+// 1e-5 relative parity bar of the float paths rules out bf16 / single-pass TF32).  Tiling: 128x128x16
+// (256 threads, 8x8 register micro-tile, double-buffered shared memory, 128-bit loads everywhere) or
+// 64x64x16 when the problem would leave SMs idle; weight-gradient launches split the position
+// dimension across CTAs and reduce the partial tiles in a fixed order.
+#include "pn2_common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---- row sources ------------------------------------------------------------------------------------
+struct RowCtx {
+  bool valid;
+  size_t off;   // element offset of the row in x (PLAIN/BNRELU/DY*: row*ld; GATHER: src*ld)
+  size_t goff;  // DYPOOL: g*ld; GATHER: source row (cloud*n_src + idx)
+  int slot;     // DYPOOL: row % group
+  float gx, gy, gz;  // GATHER: local coordinates
+};
+
+template <int KIND>
+__device__ __forceinline__ RowCtx row_ctx(const pn2_rows &s, int row) {
+  RowCtx c;
+  c.valid = row < s.rows;
+  c.off = 0; c.goff = 0; c.slot = 0; c.gx = c.gy = c.gz = 0.f;
+  if (!c.valid) return c;
+  if (KIND == PN2_ROWS_GATHER) {
+    const int cloud = row / (s.npoint * s.nsample);
+    const int centre = row / s.nsample;
+    const size_t src = static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row);
+    c.off = src * s.ld;
+    c.goff = src;
+    if (s.use_xyz) {
+      const float *p = s.xyz + src * 3, *q = s.centres + static_cast<size_t>(centre) * 3;
+      // pointnet2_utils.py:350-352: grouped_xyz -= new_xyz; grouped_xyz /= radius
+      c.gx = __fdiv_rn(__fsub_rn(__ldg(p + 0), __ldg(q + 0)), s.inv_scale);
+      c.gy = __fdiv_rn(__fsub_rn(__ldg(p + 1), __ldg(q + 1)), s.inv_scale);
+      c.gz = __fdiv_rn(__fsub_rn(__ldg(p + 2), __ldg(q + 2)), s.inv_scale);
+    }
+  } else {
+    c.off = static_cast<size_t>(row) * s.ld;
+    if (KIND == PN2_ROWS_DYPOOL) {
+      const int g = row / s.group;
+      c.goff = static_cast<size_t>(g) * s.ld;
+      c.slot = row - g * s.group;
+    }
+  }
+  return c;
+}
+
+template <int KIND>
+__device__ __forceinline__ float4 load4(const pn2_rows &s, const RowCtx &c, int c4) {
+  if (!c.valid || c4 >= s.cols) return zero4();
+  if (KIND == PN2_ROWS_PLAIN) return ldg4(s.x + c.off + c4);
+  if (KIND == PN2_ROWS_BNRELU) {
+    const float4 v = ldg4(s.x + c.off + c4), a = ldg4(s.c0 + c4), b = ldg4(s.c1 + c4);
+    return make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f),
+                       fmaxf(fmaf(v.z, a.z, b.z), 0.f), fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+  }
+  if (KIND == PN2_ROWS_GATHER) {
+    if (c4 < s.feat_cols) return ldg4(s.x + c.off + c4);
+    return make_float4(c.gx, c.gy, c.gz, 0.f);  // c4 == feat_cols: the xyz block
+  }
+  // DY / DYPOOL: dy = c0*dz + c1 + c2*y
+  const float4 y = ldg4(s.x + c.off + c4);
+  const float4 ca = ldg4(s.c0 + c4), cb = ldg4(s.c1 + c4), cc = ldg4(s.c2 + c4);
+  float4 dz;
+  if (KIND == PN2_ROWS_DY) {
+    dz = ldg4(s.dz + c.off + c4);
+  } else {
+    const float4 g = ldg4(s.dz + c.goff + c4);
+    const uchar4 a = __ldg(reinterpret_cast<const uchar4 *>(s.arg + c.goff + c4));
+    dz = make_float4(a.x == c.slot ? g.x : 0.f, a.y == c.slot ? g.y : 0.f, a.z == c.slot ? g.z : 0.f,
+                     a.w == c.slot ? g.w : 0.f);
+  }
+  return make_float4(fmaf(cc.x, y.x, fmaf(ca.x, dz.x, cb.x)), fmaf(cc.y, y.y, fmaf(ca.y, dz.y, cb.y)),
+                     fmaf(cc.z, y.z, fmaf(ca.z, dz.z, cb.z)), fmaf(cc.w, y.w, fmaf(ca.w, dz.w, cb.w)));
+}
+
+// ---- epilogues ----------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_STORE_STATS = 1, EPI_DGRAD_MASK = 2, EPI_SCATTER = 3 };
+
+struct GemmArgs {
+  pn2_rows A, B;
+  int M, N, K;          // logical extents (all multiples of 4 where they index channels)
+  int k_per_split;      // multiple of BK; blockIdx.z selects the split
+  float *out;           // [M][ldo] (+ blockIdx.z * out_split_stride)
+  int ldo;
+  long long out_split_stride;
+  float *stats;         // [gridDim.x][2][stats_ld]
+  int stats_ld;
+  // EPI_DGRAD_MASK
+  const float *prev_y, *prev_scale, *prev_shift;
+  int ld_prev;
+  // EPI_SCATTER
+  pn2_rows G;           // the forward's gather source
+  float *dfeat;
+  int ldf;
+  float *dxyz;
+  const int *centre_src;
+};
+
+template <int BM, int BN, int AKIND, bool ATRANS, int BKIND, int EPI>
+__global__ void __launch_bounds__((BM / 8) * (BN / 8), (BM == 128 ? 2 : 6))
+gemm_kernel(const __grid_constant__ GemmArgs g) {
+  constexpr int TX = BN / 8, TY = BM / 8, THREADS = TX * TY;
+  constexpr int A_LD = BM * BK / 4 / THREADS;  // float4 loads per thread per k-tile
+  constexpr int B_LD = BN * BK / 4 / THREADS;
+  constexpr int TPR = THREADS / BM;            // ATRANS: threads per A row
+  static_assert(!ATRANS || (THREADS % BM == 0 && (4 % TPR) == 0 && A_LD == 4 / TPR), "A loader mapping");
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int k_begin = blockIdx.z * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
+
+  // ATRANS: this thread always loads the same A row (a position) -> resolve its context once
+  RowCtx actx;
+  if (ATRANS) actx = row_ctx<AKIND>(g.A, m0 + tid % BM);
+
+  float4 pa[A_LD], pb[B_LD];
+  auto fetch = [&](int k0) {
+    if (ATRANS) {
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) pa[i] = load4<AKIND>(g.A, actx, k0 + ((tid / BM) * A_LD + i) * 4);
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int e = tid + i * THREADS, r = e / (BM / 4), c4 = (e % (BM / 4)) * 4;
+        const int row = k0 + r;
+        const RowCtx c = row_ctx<AKIND>(g.A, row < k_end ? row : 0x7fffffff);
+        pa[i] = load4<AKIND>(g.A, c, m0 + c4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      const int e = tid + i * THREADS, r = e / (BN / 4), c4 = (e % (BN / 4)) * 4;
+      const int row = k0 + r;
+      const RowCtx c = row_ctx<BKIND>(g.B, row < k_end ? row : 0x7fffffff);
+      pb[i] = load4<BKIND>(g.B, c, n0 + c4);
+    }
+  };
+  auto stage = [&](int buf) {
+    if (ATRANS) {
+      const int r = tid % BM;
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int kq = ((tid / BM) * A_LD + i) * 4;
+        As[buf][kq + 0][r] = pa[i].x;
+        As[buf][kq + 1][r] = pa[i].y;
+        As[buf][kq + 2][r] = pa[i].z;
+        As[buf][kq + 3][r] = pa[i].w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int e = tid + i * THREADS, r = e / (BM / 4), c4 = (e % (BM / 4)) * 4;
+        *reinterpret_cast<float4 *>(&As[buf][r][c4]) = pa[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      const int e = tid + i * THREADS, r = e / (BN / 4), c4 = (e % (BN / 4)) * 4;
+      *reinterpret_cast<float4 *>(&Bs[buf][r][c4]) = pb[i];
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  int buf = 0;
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stage(0);
+  }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][BM / 2 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][BN / 2 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) stage(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // ---- epilogue ----
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+    if (row >= g.M) continue;
+    RowCtx gctx;
+    if (EPI == EPI_SCATTER) gctx = row_ctx<PN2_ROWS_GATHER>(g.G, row);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = n0 + (h == 0 ? tx * 4 : BN / 2 + tx * 4);
+      if (col >= g.N) continue;
+      float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+      if (EPI == EPI_STORE || EPI == EPI_STORE_STATS) {
+        float *dst = g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col;
+        *reinterpret_cast<float4 *>(dst) = v;
+        if (EPI == EPI_STORE_STATS) {
+          s1[h * 4 + 0] += v.x; s1[h * 4 + 1] += v.y; s1[h * 4 + 2] += v.z; s1[h * 4 + 3] += v.w;
+          s2[h * 4 + 0] = fmaf(v.x, v.x, s2[h * 4 + 0]); s2[h * 4 + 1] = fmaf(v.y, v.y, s2[h * 4 + 1]);
+          s2[h * 4 + 2] = fmaf(v.z, v.z, s2[h * 4 + 2]); s2[h * 4 + 3] = fmaf(v.w, v.w, s2[h * 4 + 3]);
+        }
+      } else if (EPI == EPI_DGRAD_MASK) {
+        const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+        const float4 sc = ldg4(g.prev_scale + col), sh = ldg4(g.prev_shift + col);
+        v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+        v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+        v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+        v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+        *reinterpret_cast<float4 *>(g.out + static_cast<size_t>(row) * g.ldo + col) = v;
+        s1[h * 4 + 0] += v.x; s1[h * 4 + 1] += v.y; s1[h * 4 + 2] += v.z; s1[h * 4 + 3] += v.w;
+        s2[h * 4 + 0] = fmaf(v.x, y.x, s2[h * 4 + 0]); s2[h * 4 + 1] = fmaf(v.y, y.y, s2[h * 4 + 1]);
+        s2[h * 4 + 2] = fmaf(v.z, y.z, s2[h * 4 + 2]); s2[h * 4 + 3] = fmaf(v.w, y.w, s2[h * 4 + 3]);
+      } else {  // EPI_SCATTER: transpose of the gather
+        if (col < g.G.feat_cols) {
+          if (g.dfeat) {
+            float *dst = g.dfeat + gctx.goff * g.ldf + col;
+            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+          }
+        } else if (g.dxyz && g.G.use_xyz) {
+          const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                      gz = __fdiv_rn(v.z, g.G.inv_scale);
+          float *dn = g.dxyz + gctx.goff * 3;
+          atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+          const int centre = row / g.G.nsample, cloud = row / (g.G.npoint * g.G.nsample);
+          float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+          atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+        }
+      }
+    }
+  }
+
+  if (EPI == EPI_STORE_STATS || EPI == EPI_DGRAD_MASK) {
+    if (g.stats == nullptr) return;
+    // column sums over the tile's rows: registers -> shared (one row of partials per ty) -> BN threads
+    float *red = &As[0][0][0];  // 2*BK*BM floats >= TY*BN floats; second quantity goes to Bs
+    float *red2 = &Bs[0][0][0];
+    static_assert(2 * BK * BM >= TY * BN && 2 * BK * BN >= TY * BN, "reduction scratch");
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = (h == 0 ? tx * 4 : BN / 2 + tx * 4) + q;
+        red[ty * BN + c] = s1[h * 4 + q];
+        red2[ty * BN + c] = s2[h * 4 + q];
+      }
+    __syncthreads();
+    for (int c = tid; c < BN; c += THREADS) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int t = 0; t < TY; ++t) {
+        a += red[t * BN + c];
+        b += red2[t * BN + c];
+      }
+      if (n0 + c < g.stats_ld) {
+        float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + n0 + c;
+        dst[0] = a;
+        dst[g.stats_ld] = b;
+      }
+    }
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+inline bool big_tile(long long m, long long n) {
+  return ((m + 127) / 128) * ((n + 127) / 128) >= 96;  // else 64x64 tiles to keep the 148 SMs busy
+}
+
+template <int AKIND, bool ATRANS, int BKIND, int EPI>
+int launch_gemm(const GemmArgs &g, int splits, cudaStream_t stream, const char *what) {
+  if (big_tile(g.M, g.N)) {
+    dim3 grid((g.M + 127) / 128, (g.N + 127) / 128, splits);
+    gemm_kernel<128, 128, AKIND, ATRANS, BKIND, EPI><<<grid, 256, 0, stream>>>(g);
+  } else {
+    dim3 grid((g.M + 63) / 64, (g.N + 63) / 64, splits);
+    gemm_kernel<64, 64, AKIND, ATRANS, BKIND, EPI><<<grid, 64, 0, stream>>>(g);
+  }
+  return check_launch(what);
+}
+
+int check_rows(const pn2_rows *r, const char *what) {
+  PN2_REQUIRE(r != nullptr, "%s: null row source", what);
+  PN2_REQUIRE(r->rows >= 0 && r->cols >= 0 && (r->cols % 4) == 0 && (r->ld % 4) == 0, "%s: rows=%d cols=%d ld=%d must be >= 0 and multiples of 4",
+              what, r->rows, r->cols, r->ld);
+  switch (r->kind) {
+    case PN2_ROWS_PLAIN: PN2_REQUIRE(r->x, "%s: null x", what); break;
+    case PN2_ROWS_BNRELU: PN2_REQUIRE(r->x && r->c0 && r->c1, "%s: null x/scale/shift", what); break;
+    case PN2_ROWS_GATHER:
+      PN2_REQUIRE(r->idx && r->n_src > 0 && r->npoint > 0 && r->nsample > 0, "%s: bad gather geometry", what);
+      PN2_REQUIRE((r->feat_cols == 0 || r->x) && (r->feat_cols % 4) == 0, "%s: bad gather features", what);
+      PN2_REQUIRE(!r->use_xyz || (r->xyz && r->centres && r->inv_scale != 0.f), "%s: gather needs xyz/centres", what);
+      PN2_REQUIRE(r->cols == r->feat_cols + (r->use_xyz ? 4 : 0), "%s: gather cols=%d != feat_cols+4", what, r->cols);
+      break;
+    case PN2_ROWS_DY: PN2_REQUIRE(r->x && r->dz && r->c0 && r->c1 && r->c2, "%s: null dy inputs", what); break;
+    case PN2_ROWS_DYPOOL:
+      PN2_REQUIRE(r->x && r->dz && r->arg && r->c0 && r->c1 && r->c2 && r->group > 0 && r->group <= 256,
+                  "%s: bad pooled dy inputs", what);
+      break;
+    default: PN2_REQUIRE(false, "%s: unknown row source kind %d", what, r->kind);
+  }
+  return PN2_OK;
+}
+
+pn2_rows plain_rows(const float *x, int rows, int cols, int ld) {
+  pn2_rows r = {};
+  r.kind = PN2_ROWS_PLAIN;
+  r.rows = rows; r.cols = cols; r.ld = ld; r.x = x;
+  return r;
+}
+
+// ---- weight preparation / wgrad reduction -------------------------------------------------------------
+// k' (permuted, padded input channel) -> original input channel, or -1 for padding
+__device__ __forceinline__ int orig_cin(int kq, int cin, int xyz_first, int feat_pad) {
+  if (!xyz_first) return kq < cin ? kq : -1;
+  if (kq < feat_pad) return kq < cin - 3 ? kq + 3 : -1;
+  const int d = kq - feat_pad;
+  return d < 3 ? d : -1;
+}
+
+__global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np,
+                                    const float *__restrict__ w, float *__restrict__ wt, float *__restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kp * np) return;
+  {  // wt[k][n]
+    const int k = i / np, n = i % np;
+    const int c = orig_cin(k, cin, xyz_first, feat_pad);
+    wt[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+  }
+  {  // wp[n][k]
+    const int n = i / kp, k = i % kp;
+    const int c = orig_cin(k, cin, xyz_first, feat_pad);
+    wp[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+  }
+}
+
+__global__ void wgrad_reduce_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, int splits,
+                                    const float *__restrict__ ws, float *__restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * kp) return;
+  const int n = i / kp, k = i % kp;
+  const int c = orig_cin(k, cin, xyz_first, feat_pad);
+  if (c < 0) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(static_cast<size_t>(z) * np + n) * kp + k];
+  dw[static_cast<size_t>(n) * cin + c] = s;
+}
+
+int wgrad_splits(int rows, int np, int kp) {
+  const long long tiles = big_tile(np, kp) ? ((np + 127) / 128) * ((kp + 127) / 128) : ((np + 63) / 64) * ((kp + 63) / 64);
+  const int per_sm = big_tile(np, kp) ? 2 : 6;
+  long long s = (static_cast<long long>(sm_count()) * per_sm + tiles - 1) / tiles;
+  const long long max_s = (rows + 4 * BK - 1) / (4 * BK);  // at least 4 k-tiles per split
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 512) s = 512;
+  return static_cast<int>(s);
+}
+
+}  // namespace
+}  // namespace pn2
+
+using namespace pn2;
+
+PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, const float *w,
+                                    float *wt, float *wp, void *stream) {
+  PN2_REQUIRE(cout > 0 && cin > 0 && kp >= 4 && np >= cout && (kp % 4) == 0 && (np % 4) == 0 && w && wt && wp,
+              "pn2_mlp_prep_weights: bad arguments cout=%d cin=%d kp=%d np=%d", cout, cin, kp, np);
+  PN2_REQUIRE(xyz_first ? (cin >= 3 && feat_pad >= cin - 3 && kp == feat_pad + 4) : kp >= cin,
+              "pn2_mlp_prep_weights: inconsistent padding cin=%d feat_pad=%d kp=%d", cin, feat_pad, kp);
+  const int total = kp * np;
+  prep_weights_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(cout, cin, xyz_first, feat_pad,
+                                                                                       kp, np, w, wt, wp);
+  return check_launch("pn2_mlp_prep_weights");
+}
+
+PN2_EXPORT int pn2_mlp_tiles(int rows, int ncols) {
+  return big_tile(rows, ncols) ? (rows + 127) / 128 : (rows + 63) / 64;
+}
+
+PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, float *y, int ldy, float *stats,
+                               int *tiles, void *stream_) {
+  if (int rc = check_rows(a, "pn2_mlp_forward")) return rc;
+  PN2_REQUIRE(a->cols == kp && (np % 4) == 0 && np > 0 && wt && y && ldy >= np && (ldy % 4) == 0,
+              "pn2_mlp_forward: operand widths disagree (a.cols=%d kp=%d np=%d ldy=%d)", a->cols, kp, np, ldy);
+  PN2_REQUIRE(a->kind == PN2_ROWS_PLAIN || a->kind == PN2_ROWS_BNRELU || a->kind == PN2_ROWS_GATHER,
+              "pn2_mlp_forward: unsupported row source %d", a->kind);
+  if (tiles) *tiles = pn2_mlp_tiles(a->rows, np);
+  if (a->rows == 0) return PN2_OK;
+  GemmArgs g = {};
+  g.A = *a;
+  g.B = plain_rows(wt, kp, np, np);
+  g.M = a->rows; g.N = np; g.K = kp;
+  g.k_per_split = (kp + BK - 1) / BK * BK;
+  g.out = y; g.ldo = ldy;
+  g.stats = stats; g.stats_ld = np;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  switch (a->kind) {
+    case PN2_ROWS_PLAIN: return launch_gemm<PN2_ROWS_PLAIN, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
+    case PN2_ROWS_BNRELU: return launch_gemm<PN2_ROWS_BNRELU, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
+    default: return launch_gemm<PN2_ROWS_GATHER, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
+  }
+}
+
+PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, float *out, int ldo,
+                             const float *prev_y, int ld_prev, const float *prev_scale, const float *prev_shift,
+                             float *stats, int *tiles, const pn2_rows *gather, float *dfeat, int ldf, float *dxyz,
+                             const int *centre_src, void *stream_) {
+  if (int rc = check_rows(dy, "pn2_mlp_dgrad")) return rc;
+  PN2_REQUIRE(dy->kind == PN2_ROWS_DY || dy->kind == PN2_ROWS_DYPOOL, "pn2_mlp_dgrad: dy must be a DY / DYPOOL source");
+  PN2_REQUIRE(wp && ncols > 0 && (ncols % 4) == 0 && ldw >= ncols && (ldw % 4) == 0, "pn2_mlp_dgrad: bad weight operand");
+  if (tiles) *tiles = pn2_mlp_tiles(dy->rows, ncols);
+  if (dy->rows == 0) return PN2_OK;
+  GemmArgs g = {};
+  g.A = *dy;
+  g.B = plain_rows(wp, dy->cols, ncols, ldw);
+  g.M = dy->rows; g.N = ncols; g.K = dy->cols;
+  g.k_per_split = (g.K + BK - 1) / BK * BK;
+  g.out = out; g.ldo = ldo;
+  g.stats = stats; g.stats_ld = ncols;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const bool pool = dy->kind == PN2_ROWS_DYPOOL;
+  if (mode == PN2_DGRAD_MASK) {
+    PN2_REQUIRE(out && prev_y && prev_scale && prev_shift && ldo >= ncols && ld_prev >= ncols, "pn2_mlp_dgrad: MASK needs out/prev_*");
+    g.prev_y = prev_y; g.prev_scale = prev_scale; g.prev_shift = prev_shift; g.ld_prev = ld_prev;
+    return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_DGRAD_MASK>(g, 1, s, "pn2_mlp_dgrad")
+                : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_DGRAD_MASK>(g, 1, s, "pn2_mlp_dgrad");
+  }
+  if (mode == PN2_DGRAD_STORE) {
+    PN2_REQUIRE(out && ldo >= ncols, "pn2_mlp_dgrad: STORE needs out");
+    return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_STORE>(g, 1, s, "pn2_mlp_dgrad")
+                : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_STORE>(g, 1, s, "pn2_mlp_dgrad");
+  }
+  PN2_REQUIRE(mode == PN2_DGRAD_SCATTER, "pn2_mlp_dgrad: unknown mode %d", mode);
+  if (int rc = check_rows(gather, "pn2_mlp_dgrad(gather)")) return rc;
+  PN2_REQUIRE(gather->kind == PN2_ROWS_GATHER && gather->rows == dy->rows && gather->cols == ncols,
+              "pn2_mlp_dgrad: gather source does not match (rows %d vs %d, cols %d vs %d)", gather->rows, dy->rows,
+              gather->cols, ncols);
+  PN2_REQUIRE((dfeat == nullptr || ldf >= gather->feat_cols) && (dxyz == nullptr || centre_src != nullptr),
+              "pn2_mlp_dgrad: SCATTER targets inconsistent");
+  g.G = *gather; g.dfeat = dfeat; g.ldf = ldf; g.dxyz = dxyz; g.centre_src = centre_src;
+  return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_SCATTER>(g, 1, s, "pn2_mlp_dgrad")
+              : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_SCATTER>(g, 1, s, "pn2_mlp_dgrad");
+}
+
+PN2_EXPORT long long pn2_mlp_wgrad_workspace(int rows, int np, int kp) {
+  return static_cast<long long>(wgrad_splits(rows, np, kp)) * np * kp;
+}
+
+PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, int cin, int xyz_first, int feat_pad,
+                             float *ws, float *dw, void *stream_) {
+  if (int rc = check_rows(dy, "pn2_mlp_wgrad(dy)")) return rc;
+  if (int rc = check_rows(a, "pn2_mlp_wgrad(a)")) return rc;
+  PN2_REQUIRE(dy->kind == PN2_ROWS_DY || dy->kind == PN2_ROWS_DYPOOL, "pn2_mlp_wgrad: dy must be a DY / DYPOOL source");
+  PN2_REQUIRE(a->kind == PN2_ROWS_PLAIN || a->kind == PN2_ROWS_BNRELU || a->kind == PN2_ROWS_GATHER,
+              "pn2_mlp_wgrad: unsupported activation source %d", a->kind);
+  PN2_REQUIRE(dy->rows == a->rows && ws && dw && cout <= dy->cols && cin <= a->cols, "pn2_mlp_wgrad: shapes disagree");
+  const int np = dy->cols, kp = a->cols, rows = dy->rows;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int splits = wgrad_splits(rows, np, kp);
+  GemmArgs g = {};
+  g.A = *dy; g.B = *a;
+  g.M = np; g.N = kp; g.K = rows;
+  g.k_per_split = ((rows + splits - 1) / splits + BK - 1) / BK * BK;
+  g.out = ws; g.ldo = kp; g.out_split_stride = static_cast<long long>(np) * kp;
+  int rc = PN2_OK;
+  if (rows > 0) {
+#define PN2_WGRAD(DK, AK) launch_gemm<DK, false, AK, EPI_STORE>(g, splits, s, "pn2_mlp_wgrad")
+    const bool pool = dy->kind == PN2_ROWS_DYPOOL;
+    switch (a->kind) {
+      case PN2_ROWS_PLAIN: rc = pool ? PN2_WGRAD(PN2_ROWS_DYPOOL, PN2_ROWS_PLAIN) : PN2_WGRAD(PN2_ROWS_DY, PN2_ROWS_PLAIN); break;
+      case PN2_ROWS_BNRELU: rc = pool ? PN2_WGRAD(PN2_ROWS_DYPOOL, PN2_ROWS_BNRELU) : PN2_WGRAD(PN2_ROWS_DY, PN2_ROWS_BNRELU); break;
+      default: rc = pool ? PN2_WGRAD(PN2_ROWS_DYPOOL, PN2_ROWS_GATHER) : PN2_WGRAD(PN2_ROWS_DY, PN2_ROWS_GATHER); break;
+    }
+#undef PN2_WGRAD
+    if (rc) return rc;
+  }
+  const int total = cout * kp;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(cout, cin, xyz_first, feat_pad, kp, np, rows > 0 ? splits : 0, ws, dw);
+  return check_launch("pn2_mlp_wgrad(reduce)");
+}

@@ -1,17 +1,325 @@
-"""Fused set-abstraction / feature-propagation path (filled in once the MLP kernels land)."""
+"""Fused set-abstraction / feature-propagation execution on libpn2_b200.so.
+
+Replaces, for `PointnetSAModuleVotes` (max pooling) and `PointnetFPModule`, the chain the reference runs
+as ~20 separate kernels per layer (pointnet2_modules.py:233-267 / :393-416 -> pointnet2_utils.py:334-359
+-> pytorch_utils.py SharedMLP -> cuDNN/ATen), including its autograd backward:
+
+    SA forward :  FPS(+centre gather)  ->  ball query  ->  [gather+centre-subtract fused into GEMM 0]
+                  -> BN stats -> [BN+ReLU fused into GEMM l's operand load] ... -> BN+ReLU+max-pool
+    FP forward :  three_nn + weights + interpolate (one gather-MAC kernel) -> same MLP chain
+    backward   :  pool/ReLU/BN backward folded into the operand loads of the dgrad / wgrad GEMMs,
+                  scatter-add into the gathered inputs in the last dgrad's epilogue.
+
+Activations live position-major ([rows, channels], channels padded to a multiple of 4); the API tensors
+keep the reference's (B,C,N) layout, and a module output remembers its position-major twin
+(`tensor._pn2_pm`) so the next module does not transpose it back.
+
+torch is used for memory, streams, autograd bookkeeping and (SyncBatchNorm only) the cross-rank
+all-reduce of the BatchNorm sums; every computation is a libpn2_b200 kernel.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+import _pn2 as K
+
+pad4 = K.pad4
+
+
+# ---- what the fused path accepts ------------------------------------------------------------------------
+def _mlp_layers(shared_mlp):
+    """[(conv, bn)] if every unit is Conv2d 1x1 (no bias) -> BatchNorm -> ReLU, else None."""
+    layers = []
+    for unit in shared_mlp.children():
+        mods = list(unit.children())
+        if len(mods) != 3:
+            return None
+        conv, bnw, act = mods
+        if not isinstance(conv, nn.Conv2d) or conv.bias is not None or conv.kernel_size != (1, 1):
+            return None
+        if conv.stride != (1, 1) or conv.padding != (0, 0) or conv.groups != 1:
+            return None
+        bn = list(bnw.children())[0] if isinstance(bnw, nn.Sequential) and len(list(bnw.children())) == 1 else bnw
+        if not isinstance(bn, nn.modules.batchnorm._BatchNorm) or not bn.affine:
+            return None
+        if not bn.training and bn.running_mean is None:
+            return None
+        if not isinstance(act, nn.ReLU):
+            return None
+        layers.append((conv, bn))
+    return layers or None
+
+
+def _ok_tensor(t):
+    return t is not None and t.is_cuda and t.dtype == torch.float32
 
 
 def sa_supported(module, xyz, features):
-    return False
+    if module.npoint is None or module.pooling != 'max' or module.ret_unique_cnt:
+        return False
+    if getattr(module.grouper, "sample_uniformly", False):
+        return False
+    if not _ok_tensor(xyz) or (features is not None and not _ok_tensor(features)):
+        return False
+    if features is None and not module.use_xyz:
+        return False
+    if not (0 < module.nsample <= 256):
+        return False
+    return _mlp_layers(module.mlp_module) is not None
 
 
 def fp_supported(module, unknown, known, unknow_feats, known_feats):
-    return False
+    if known is None or not _ok_tensor(unknown) or not _ok_tensor(known) or not _ok_tensor(known_feats):
+        return False
+    if unknow_feats is not None and (not _ok_tensor(unknow_feats) or known_feats.shape[1] % 4 != 0):
+        return False
+    return _mlp_layers(module.mlp) is not None
+
+
+# ---- helpers -------------------------------------------------------------------------------------------
+def _cached_pm(features):
+    """Position-major twin remembered by the module that produced `features` (None if absent / stale)."""
+    cache = getattr(features, "_pn2_pm", None) if features is not None else None
+    if cache is not None and cache[1] == features._version and cache[2] == tuple(features.shape):
+        return cache[0]
+    return None
+
+
+def _point_major(features, cached):
+    return cached if cached is not None else K.to_point_major(features.detach().contiguous())
+
+
+def _remember_pm(out, out_pm):
+    out._pn2_pm = (out_pm.detach(), out._version, tuple(out.shape))
+
+
+def _sync_group(bn):
+    """Process group to all-reduce BatchNorm sums over, or None (plain BatchNorm / single rank)."""
+    if not isinstance(bn, nn.SyncBatchNorm) or not bn.training:
+        return None
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
+
+
+class _Layer:
+    """Per-layer forward state kept for the backward pass."""
+    __slots__ = ("cout", "cin", "kp", "np", "xyz_first", "feat_pad", "wt", "wp", "y", "scale", "shift", "mean",
+                 "invstd", "training", "count", "group", "gamma")
+
+
+def _bn_forward(L, bn, stats, tiles, rows):
+    """BatchNorm statistics of L.y -> folded scale/shift (running stats in eval mode)."""
+    training = bn.training
+    L.training, L.group, L.gamma = training, None, bn.weight
+    count, sums = float(rows), None
+    if training:
+        pg = _sync_group(bn)
+        if pg is not None:
+            sums = K.bn_reduce_stats(stats, tiles, L.cout, L.np)
+            cnt = torch.tensor([float(rows)], dtype=torch.float64, device=sums.device)
+            dist.all_reduce(sums, group=pg)
+            dist.all_reduce(cnt, group=pg)
+            count = float(cnt.item())
+            L.group = pg
+        if count <= 1:
+            raise ValueError("Expected more than 1 value per channel when training")
+    L.count = count
+    L.scale, L.shift, L.mean, L.invstd = K.bn_finalize(training, tiles, L.cout, L.np, count, stats, sums, bn)
+
+
+def _run_mlp(layers, rows0, nrows, xyz_first, feat_pad, need_grad):
+    """Forward through the conv+BN(+ReLU) stack; returns the per-layer state list."""
+    state = []
+    src, kp = rows0, rows0.cols
+    for li, (conv, bn) in enumerate(layers):
+        L = _Layer()
+        L.cout, L.cin = conv.weight.shape[0], conv.weight.shape[1]
+        L.kp, L.np = kp, pad4(L.cout)
+        L.xyz_first, L.feat_pad = (xyz_first, feat_pad) if li == 0 else (0, 0)
+        L.wt, L.wp = K.mlp_prep_weights(conv.weight.detach().view(L.cout, L.cin), L.xyz_first, L.feat_pad, L.kp, L.np)
+        L.y, stats, tiles = K.mlp_forward(src, L.kp, L.np, L.wt, want_stats=bn.training)
+        _bn_forward(L, bn, stats, tiles, nrows)
+        state.append(L)
+        src, kp = K.rows_bnrelu(L.y, nrows, L.np, L.np, L.scale, L.shift), L.np
+    return state
+
+
+def _bn_backward(L, stats, tiles):
+    """-> (ca, cb, cc, dgamma, dbeta) for dy = ca*dz + cb + cc*y."""
+    sums = None
+    if L.group is not None:
+        sums = K.bn_reduce_stats(stats, tiles, L.cout, L.np)
+        dist.all_reduce(sums, group=L.group)
+    return K.bn_bwd_finalize(L.training, tiles, L.cout, L.np, L.count, stats, sums, L.gamma.detach(), L.mean, L.invstd)
+
+
+def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
+    """Backward through the stack.  gz: position-major grad of the pooled output [groups, np_last]
+    (overwritten).  first_dgrad(dy, L0) handles the input gradient of layer 0.  Returns the parameter
+    gradients [(dW, dgamma, dbeta)] in layer order."""
+    last = state[-1]
+    groups = nrows // group
+    stats, tiles = K.pool_bwd_prep(gz, out_pm, arg, last.y, groups, group, last.cout, last.np)
+    ca, cb, cc, dgamma, dbeta = _bn_backward(last, stats, tiles)
+    dy = K.rows_dy(last.y, gz, nrows, last.np, last.np, ca, cb, cc, arg=arg, group=group)
+    grads = [None] * len(state)
+    for li in range(len(state) - 1, -1, -1):
+        L = state[li]
+        if li > 0:
+            P = state[li - 1]
+            a_src = K.rows_bnrelu(P.y, nrows, P.np, P.np, P.scale, P.shift)
+        else:
+            a_src = rows0
+        dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device)
+        grads[li] = (dw.view(L.cout, L.cin, 1, 1), dgamma, dbeta)
+        if li > 0:
+            dz, stats, tiles = K.mlp_dgrad_mask(dy, P.np, L.wp, P.y, P.scale, P.shift)
+            ca, cb, cc, dgamma, dbeta = _bn_backward(P, stats, tiles)
+            dy = K.rows_dy(P.y, dz, nrows, P.np, P.np, ca, cb, cc)
+        else:
+            first_dgrad(dy, L)
+    return grads
+
+
+def _flat_params(layers):
+    out = []
+    for conv, bn in layers:
+        out += [conv.weight, bn.weight, bn.bias]
+    return out
+
+
+# ---- set abstraction -------------------------------------------------------------------------------------
+class _SAFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, layers, feat_cached, xyz, features, inds, *params):
+        b, n, _ = xyz.shape
+        m, ns = module.npoint, module.nsample
+        xyz_c = xyz.detach().contiguous()
+        if inds is None:
+            inds, new_xyz = K.furthest_point_sampling(xyz_c, m, return_xyz=True)
+        else:
+            inds = inds.contiguous()
+            new_xyz = K.gather_points(xyz_c.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+        idx = K.ball_query(new_xyz, xyz_c, module.radius, ns)
+        if features is not None:
+            c_feat = features.shape[1]
+            feat_pm = _point_major(features, feat_cached)
+            ldf = feat_pm.shape[1]
+        else:
+            c_feat, feat_pm, ldf = 0, None, 0
+        use_xyz = bool(module.use_xyz)
+        inv_scale = module.radius if module.normalize_xyz else 1.0
+        rows0 = K.rows_gather(feat_pm, ldf, ldf, idx, xyz_c, new_xyz, n, m, ns, use_xyz, inv_scale)
+        nrows = b * m * ns
+        need_grad = any(ctx.needs_input_grad)
+        state = _run_mlp(layers, rows0, nrows, 1 if use_xyz else 0, ldf, need_grad)
+        last = state[-1]
+        out_pm, arg = K.bn_relu_pool(last.y, b * m, ns, last.cout, last.np, last.scale, last.shift)
+        out = K.to_channel_major(out_pm, b, last.cout, m)
+        ctx.pn2 = (state, rows0, nrows, out_pm, arg, (b, n, m, ns, c_feat, ldf), inds)
+        ctx.mark_non_differentiable(inds, out_pm)
+        ctx.set_materialize_grads(False)
+        return new_xyz, out, inds, out_pm
+
+    @staticmethod
+    def backward(ctx, g_new_xyz, g_out, _g_inds, _g_pm):
+        state, rows0, nrows, out_pm, arg, (b, n, m, ns, c_feat, ldf), inds = ctx.pn2
+        need_xyz, need_feat = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        dev = out_pm.device
+        dxyz = dfeat = None
+        grads = [None] * (3 * len(state))
+        if g_out is not None:
+            last = state[-1]
+            gz = K.to_point_major(g_out.contiguous(), ld=last.np)
+            dfeat_pm = K._f32(dev, b * n, ldf, zero=True) if (need_feat and c_feat) else None
+            dxyz_pm = K._f32(dev, b * n, 3, zero=True) if (need_xyz and rows0.use_xyz) else None
+
+            def first_dgrad(dy, L0):
+                if dfeat_pm is not None or dxyz_pm is not None:
+                    K.mlp_dgrad_scatter(dy, L0.kp, L0.wp, rows0, dfeat_pm, dxyz_pm, inds)
+
+            per_layer = _mlp_backward(state, rows0, nrows, gz, out_pm, arg, ns, first_dgrad)
+            grads = [g for triple in per_layer for g in triple]
+            if dfeat_pm is not None:
+                dfeat = K.to_channel_major(dfeat_pm, b, c_feat, n)
+            if dxyz_pm is not None:
+                dxyz = dxyz_pm.view(b, n, 3)
+        if need_xyz and g_new_xyz is not None:
+            # new_xyz = xyz[inds]: scatter-add its gradient back (GatherOperation.backward in the reference)
+            g = K.gather_points_grad(g_new_xyz.transpose(1, 2).contiguous(), inds, n).transpose(1, 2)
+            dxyz = g if dxyz is None else dxyz + g
+        if need_xyz and dxyz is None:
+            dxyz = torch.zeros(b, n, 3, dtype=torch.float32, device=dev)
+        return (None, None, None, dxyz, dfeat, None, *grads)
 
 
 def sa_forward(module, xyz, features, inds):
-    raise NotImplementedError
+    layers = _mlp_layers(module.mlp_module)
+    new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), xyz, features, inds,
+                                                   *_flat_params(layers))
+    _remember_pm(out, out_pm)
+    return new_xyz, out, inds
+
+
+# ---- feature propagation -----------------------------------------------------------------------------------
+class _FPFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, layers, known_cached, unknown, known, unknow_feats, known_feats, *params):
+        b, n, _ = unknown.shape
+        m = known.shape[1]
+        c2 = known_feats.shape[1]
+        known_pm = _point_major(known_feats, known_cached)
+        ld2 = known_pm.shape[1]
+        c1 = unknow_feats.shape[1] if unknow_feats is not None else 0
+        ld1 = pad4(c1)
+        ldx = ld2 + ld1
+        x = K._f32(unknown.device, b * n, ldx)
+        idx, weight = K.fp_interpolate(unknown.detach().contiguous(), known.detach().contiguous(), known_pm, ld2, x, ldx)
+        if c1:
+            K.to_point_major(unknow_feats.detach().contiguous(), ld=ld1, out=x, col0=ld2)
+        nrows = b * n
+        rows0 = K.rows_plain(x, nrows, ldx, ldx)
+        state = _run_mlp(layers, rows0, nrows, 0, 0, any(ctx.needs_input_grad))
+        last = state[-1]
+        out_pm, _ = K.bn_relu_pool(last.y, nrows, 1, last.cout, last.np, last.scale, last.shift, want_arg=False)
+        out = K.to_channel_major(out_pm, b, last.cout, n)
+        ctx.pn2 = (state, rows0, nrows, out_pm, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx))
+        ctx.mark_non_differentiable(out_pm)
+        ctx.set_materialize_grads(False)
+        return out, out_pm
+
+    @staticmethod
+    def backward(ctx, g_out, _g_pm):
+        state, rows0, nrows, out_pm, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx) = ctx.pn2
+        need_unknow, need_known = ctx.needs_input_grad[5], ctx.needs_input_grad[6]
+        if g_out is None:
+            return (None,) * (7 + 3 * len(state))
+        last = state[-1]
+        gz = K.to_point_major(g_out.contiguous(), ld=last.np)
+        box = {}
+
+        def first_dgrad(dy, L0):
+            if need_unknow or need_known:
+                box["dx"] = K.mlp_dgrad_store(dy, ldx, L0.wp)
+
+        per_layer = _mlp_backward(state, rows0, nrows, gz, out_pm, None, 1, first_dgrad)
+        grads = [g for triple in per_layer for g in triple]
+        d_unknow = d_known = None
+        if "dx" in box:
+            dx = box["dx"]
+            if need_known:
+                dk_pm = K.fp_interpolate_grad(dx, ldx, idx, weight, b, n, m, ld2, ld2)
+                d_known = K.to_channel_major(dk_pm, b, c2, m)
+            if need_unknow and c1:
+                d_unknow = K.to_channel_major(dx, b, c1, n, col0=ld2)
+        return (None, None, None, None, None, d_unknow, d_known, *grads)
 
 
 def fp_forward(module, unknown, known, unknow_feats, known_feats):
-    raise NotImplementedError
+    layers = _mlp_layers(module.mlp)
+    out, out_pm = _FPFunction.apply(module, layers, _cached_pm(known_feats), unknown, known, unknow_feats, known_feats,
+                                    *_flat_params(layers))
+    _remember_pm(out, out_pm)
+    return out
