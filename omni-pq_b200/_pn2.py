@@ -37,11 +37,50 @@ _f = ctypes.c_float
 launch_count = 0
 
 
-def _sig(name, *argtypes):
+# ---- optional per-launch CUDA-event timing (bench.py's roofline pass) ----------------------------------
+_prof = None          # list of (label, start_event, end_event, flops, bytes) while profiling
+_work = (None, 0.0, 0.0)
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> [(label, milliseconds, algorithmic flops, algorithmic bytes)] (call after a synchronize)."""
+    global _prof
+    recs, _prof = _prof, None
+    return [(lbl, s.elapsed_time(e), fl, by) for lbl, s, e, fl, by in recs]
+
+
+def _annotate(label, flops=0.0, nbytes=0.0):
+    """Describe the next launch for the profile: a label and its algorithmic work."""
+    global _work
+    if _prof is not None:
+        _work = (label, float(flops), float(nbytes))
+
+
+def _sig(name, *argtypes, kernel=True):
     fn = getattr(lib, name)
     fn.argtypes = list(argtypes)
     fn.restype = ctypes.c_int
-    return fn
+    if not kernel:
+        return fn
+
+    def call(*args):
+        global _work
+        if _prof is None:
+            return fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _prof.append((_work[0] or name, s, e, _work[1], _work[2]))
+        _work = (None, 0.0, 0.0)
+        return rc
+
+    return call
 
 
 def _check(rc):
@@ -111,6 +150,7 @@ def furthest_point_sampling(points, nsamples, return_xyz=False):
         tmp = None
         if n > lib.pn2_fps_resident_capacity():
             tmp = torch.empty(b, n, dtype=torch.float32, device=points.device)
+        _annotate("fps_kernel", nbytes=b * (12.0 * n + 16.0 * nsamples))
         _check(_fps(b, n, nsamples, _ptr(points), _ptr(tmp) if tmp is not None else None, _ptr(out),
                     _ptr(new_xyz) if return_xyz else None, _stream()))
     _launched()
@@ -153,6 +193,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     n = xyz.shape[1]
     with torch.cuda.device(xyz.device):
         idx = torch.empty(b, m, int(nsample), dtype=torch.int32, device=xyz.device)
+        _annotate("ball_query_kernel", nbytes=b * (12.0 * (n + m) + 4.0 * m * int(nsample)))
         _check(_ball(b, n, m, float(radius), int(nsample), _ptr(new_xyz), _ptr(xyz), _ptr(idx), _stream()))
     _launched()
     return idx
@@ -289,14 +330,14 @@ _ip_ = ctypes.POINTER(ctypes.c_int)
 _d = ctypes.c_double
 _prep = _sig("pn2_mlp_prep_weights", _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
 _mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _i, _vp, _ip_, _vp)
-_mlp_tiles = _sig("pn2_mlp_tiles", _i, _i)
+_mlp_tiles = _sig("pn2_mlp_tiles", _i, _i, kernel=False)
 _bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _vp, _vp, _vp)
 _bn_fin = _sig("pn2_bn_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp)
 _pool = _sig("pn2_bn_relu_pool", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
 _to_pm = _sig("pn2_to_point_major", _i, _i, _i, _i, _i, _vp, _vp, _vp)
 _to_cm = _sig("pn2_to_channel_major", _i, _i, _i, _i, _vp, _vp, _vp)
 _pool_prep = _sig("pn2_pool_bwd_prep", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip_, _vp)
-_pool_tiles = _sig("pn2_pool_bwd_tiles", _i)
+_pool_tiles = _sig("pn2_pool_bwd_tiles", _i, kernel=False)
 _bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
 _wgrad = _sig("pn2_mlp_wgrad", _rp, _rp, _i, _i, _i, _i, _vp, _vp, _vp)
@@ -306,8 +347,14 @@ _fp_interp = _sig("pn2_fp_interpolate", _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, 
 _fp_interp_grad = _sig("pn2_fp_interpolate_grad", _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp)
 
 
+_POISON = bool(os.environ.get("PN2_DEBUG_POISON"))  # debugging aid: NaN-fill every scratch/output buffer
+
+
 def _f32(dev, *shape, zero=False):
-    return (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=dev)
+    t = (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=dev)
+    if _POISON and not zero:
+        t.fill_(float("nan"))
+    return t
 
 
 def mlp_prep_weights(w2d, xyz_first, feat_pad, kp, np_):
@@ -325,6 +372,7 @@ def mlp_forward(rows, kp, np_, wt, want_stats=True):
     tiles = _mlp_tiles(rows.rows, np_)
     stats = _f32(dev, max(tiles, 1), 2, np_) if want_stats else None
     t = ctypes.c_int(0)
+    _annotate("gemm_kernel<forward>", flops=2.0 * rows.rows * kp * np_, nbytes=4.0 * rows.rows * (kp + np_))
     _check(_mlp_fwd(ctypes.byref(rows), kp, np_, _ptr(wt), _ptr(y), np_, _p(stats), ctypes.byref(t), _stream()))
     _launched()
     return y, stats, tiles
@@ -355,6 +403,7 @@ def bn_finalize(training, tiles, c, np_, count, stats, sums, bn):
 def bn_relu_pool(y, groups, group, c, ld, scale, shift, want_arg=True):
     out_pm = _f32(y.device, groups, ld)
     arg = torch.empty(groups, ld, dtype=torch.uint8, device=y.device) if want_arg else None
+    _annotate("bn_relu_pool_kernel", nbytes=4.0 * groups * ld * (group + 1.25))
     _check(_pool(groups, group, c, ld, _ptr(y), _ptr(scale), _ptr(shift), _ptr(out_pm), _p(arg), _stream()))
     _launched()
     return out_pm, arg
@@ -367,6 +416,7 @@ def to_point_major(src, ld=None, out=None, col0=0):
     if out is None:
         out = _f32(src.device, b * n, ld)
     stride = out.shape[1]
+    _annotate("to_point_major_kernel", nbytes=8.0 * b * c * n)
     _check(_to_pm(b, c, n, ld, stride, _ptr(src), _vp(out.data_ptr() + 4 * col0), _stream()))
     _launched()
     return out
@@ -375,6 +425,7 @@ def to_point_major(src, ld=None, out=None, col0=0):
 def to_channel_major(src_pm, b, c, n, col0=0):
     """[B*N, stride] (columns col0..col0+c) -> (B,C,N)."""
     out = _f32(src_pm.device, b, c, n)
+    _annotate("to_channel_major_kernel", nbytes=8.0 * b * c * n)
     _check(_to_cm(b, c, n, src_pm.shape[1], _vp(src_pm.data_ptr() + 4 * col0), _ptr(out), _stream()))
     _launched()
     return out
@@ -384,6 +435,7 @@ def pool_bwd_prep(gz, out_pm, arg, y, groups, group, c, ld):
     tiles = _pool_tiles(groups)
     stats = _f32(gz.device, max(tiles, 1), 2, ld)
     t = ctypes.c_int(0)
+    _annotate("pool_bwd_prep_kernel", nbytes=4.0 * groups * ld * 4.25)
     _check(_pool_prep(groups, group, c, ld, _ptr(gz), _ptr(out_pm), _p(arg), _ptr(y), _ptr(stats), ctypes.byref(t),
                       _stream()))
     _launched()
@@ -408,6 +460,7 @@ def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift):
     tiles = _mlp_tiles(dy.rows, ncols)
     stats = _f32(dev, max(tiles, 1), 2, ncols)
     t = ctypes.c_int(0)
+    _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + 2 * ncols))
     _check(_dgrad(DGRAD_MASK, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, _ptr(prev_y),
                   prev_y.shape[1], _ptr(prev_scale), _ptr(prev_shift), _ptr(stats), ctypes.byref(t), None, None, 0,
                   None, None, _stream()))
@@ -417,6 +470,7 @@ def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift):
 
 def mlp_dgrad_store(dy, ncols, wp):
     out = _f32(wp.device, dy.rows, ncols)
+    _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
     _check(_dgrad(DGRAD_STORE, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, None, 0, None, None,
                   None, None, None, None, 0, None, None, _stream()))
     _launched()
@@ -424,6 +478,7 @@ def mlp_dgrad_store(dy, ncols, wp):
 
 
 def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src):
+    _annotate("gemm_kernel<dgrad+scatter>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
     _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], None, 0, None, 0, None, None, None,
                   None, ctypes.byref(gather), _p(dfeat), dfeat.shape[1] if dfeat is not None else 0, _p(dxyz),
                   _p(centre_src), _stream()))
@@ -433,6 +488,7 @@ def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src):
 def mlp_wgrad(dy, a, cout, cin, xyz_first, feat_pad, dev):
     ws = _f32(dev, max(1, lib.pn2_mlp_wgrad_workspace(dy.rows, dy.cols, a.cols)))
     dw = _f32(dev, cout, cin)
+    _annotate("gemm_kernel<wgrad>", flops=2.0 * dy.rows * dy.cols * a.cols, nbytes=4.0 * dy.rows * (2 * dy.cols + a.cols))
     _check(_wgrad(ctypes.byref(dy), ctypes.byref(a), cout, cin, int(xyz_first), feat_pad, _ptr(ws), _ptr(dw), _stream()))
     _launched(2)
     return dw
@@ -444,6 +500,7 @@ def fp_interpolate(unknown, known, known_pm, c, out, ldo):
     m = known.shape[1]
     idx = torch.empty(b, n, 3, dtype=torch.int32, device=unknown.device)
     w = _f32(unknown.device, b, n, 3)
+    _annotate("fp_interpolate_kernel", nbytes=4.0 * b * (3.0 * (n + m) + n * (4.0 * c + 6)))
     _check(_fp_interp(b, n, m, c, known_pm.shape[1], _ptr(unknown), _ptr(known), _ptr(known_pm), _ptr(out), ldo,
                       _ptr(idx), _ptr(w), _stream()))
     _launched()

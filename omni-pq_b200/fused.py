@@ -46,6 +46,8 @@ def _mlp_layers(shared_mlp):
             return None
         if not isinstance(act, nn.ReLU):
             return None
+        if not (conv.weight.is_cuda and bn.weight.is_cuda and (bn.running_mean is None or bn.running_mean.is_cuda)):
+            return None  # parameters / buffers must live on the GPU like the inputs
         layers.append((conv, bn))
     return layers or None
 
