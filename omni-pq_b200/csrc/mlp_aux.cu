@@ -59,21 +59,41 @@ to_channel_major_kernel(int c, int n, int stride, const float *__restrict__ src,
 }
 
 // ---- BatchNorm statistics ---------------------------------------------------------------------------
-// stats[tiles][2][np] fp32 partials -> fp64 totals (fixed order => deterministic)
-__device__ __forceinline__ void total_of(const float *stats, int tiles, int np, int ch, double &s1, double &s2) {
+// stats[tiles][2][np] fp32 partials -> fp64 totals.  Block = 32 channels x 8 tile lanes: lane ty walks
+// tiles ty, ty+8, ... (coalesced across the 32 channels), the 8 lane totals are combined in a fixed
+// order through shared memory, so the result is deterministic.  Every thread with ty == 0 gets the totals.
+constexpr int kStatCh = 32, kStatLanes = 8;
+
+__device__ __forceinline__ void total_of(const float *stats, int tiles, int np, int ch, bool live, double &s1,
+                                         double &s2) {
+  __shared__ double red[2][kStatLanes][kStatCh];
+  const int tx = threadIdx.x % kStatCh, ty = threadIdx.x / kStatCh;
+  double a = 0.0, b = 0.0;
+  if (live && stats) {
+    for (int t = ty; t < tiles; t += kStatLanes) {
+      a += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 0) * np + ch]);
+      b += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 1) * np + ch]);
+    }
+  }
+  red[0][ty][tx] = a;
+  red[1][ty][tx] = b;
+  __syncthreads();
   s1 = 0.0; s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    s1 += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 0) * np + ch]);
-    s2 += static_cast<double>(stats[(static_cast<size_t>(t) * 2 + 1) * np + ch]);
+  if (ty == 0) {
+#pragma unroll
+    for (int l = 0; l < kStatLanes; ++l) {
+      s1 += red[0][l][tx];
+      s2 += red[1][l][tx];
+    }
   }
 }
 
-__global__ void bn_reduce_stats_kernel(int tiles, int c, int np, const float *__restrict__ stats,
-                                       double *__restrict__ sums) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+__global__ void __launch_bounds__(kStatCh * kStatLanes)
+bn_reduce_stats_kernel(int tiles, int c, int np, const float *__restrict__ stats, double *__restrict__ sums) {
+  const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
   double s1, s2;
-  total_of(stats, tiles, np, ch, s1, s2);
+  total_of(stats, tiles, np, ch, ch < c, s1, s2);
+  if (threadIdx.x / kStatCh != 0 || ch >= c) return;
   sums[ch] = s1;
   sums[c + ch] = s2;
 }
@@ -85,17 +105,17 @@ __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, doubl
                                    long long *__restrict__ nbt, float momentum, float eps, float *__restrict__ scale,
                                    float *__restrict__ shift, float *__restrict__ mean_out,
                                    float *__restrict__ invstd_out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= np) return;
+  const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
+  double s1 = 0.0, s2 = 0.0;
+  if (training && !sums) total_of(stats, tiles, np, ch, ch < c, s1, s2);  // block-cooperative: before any return
+  if (threadIdx.x / kStatCh != 0 || ch >= np) return;
   if (ch >= c) {  // zero padding: padded channels stay exactly 0 through BN+ReLU
     scale[ch] = 0.f; shift[ch] = 0.f; mean_out[ch] = 0.f; invstd_out[ch] = 0.f;
     return;
   }
   float mean, invstd;
   if (training) {
-    double s1, s2;
     if (sums) { s1 = sums[ch]; s2 = sums[c + ch]; }
-    else total_of(stats, tiles, np, ch, s1, s2);
     const double mu = s1 / count;
     double var = s2 / count - mu * mu;  // biased variance (what BatchNorm normalises with)
     if (var < 0.0) var = 0.0;
@@ -129,15 +149,15 @@ __global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, d
                                        const float *__restrict__ invstd, float *__restrict__ ca,
                                        float *__restrict__ cb, float *__restrict__ cc, float *__restrict__ dgamma,
                                        float *__restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= np) return;
+  const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
+  double s_dz = 0.0, s_dzy = 0.0;
+  if (!sums) total_of(stats, tiles, np, ch, ch < c, s_dz, s_dzy);  // block-cooperative: before any return
+  if (threadIdx.x / kStatCh != 0 || ch >= np) return;
   if (ch >= c) {
     ca[ch] = 0.f; cb[ch] = 0.f; cc[ch] = 0.f;
     return;
   }
-  double s_dz, s_dzy;
   if (sums) { s_dz = sums[ch]; s_dzy = sums[c + ch]; }
-  else total_of(stats, tiles, np, ch, s_dz, s_dzy);
   const double mu = mean[ch], r = invstd[ch], gmm = gamma ? gamma[ch] : 1.0;
   const double s_dzn = r * (s_dzy - mu * s_dz);  // sum dz * normalised y
   if (dgamma) dgamma[ch] = static_cast<float>(s_dzn);
@@ -348,7 +368,7 @@ PN2_EXPORT int pn2_to_channel_major(int b, int c, int n, int stride, const float
 
 PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream) {
   PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
-  bn_reduce_stats_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(tiles, c, np, stats, sums);
+  bn_reduce_stats_kernel<<<(c + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, static_cast<cudaStream_t>(stream)>>>(tiles, c, np, stats, sums);
   return check_launch("pn2_bn_reduce_stats");
 }
 
@@ -360,7 +380,7 @@ PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double co
   PN2_REQUIRE(training ? ((stats || sums) && count > 0.0) : (running_mean && running_var),
               "pn2_bn_finalize: %s", training ? "training needs statistics and a positive count" : "eval needs running statistics");
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(np + 127) / 128, 128, 0, s>>>(training, tiles, c, np, count, stats, sums, gamma, beta,
+  bn_finalize_kernel<<<(np + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, s>>>(training, tiles, c, np, count, stats, sums, gamma, beta,
                                                        running_mean, running_var, num_batches_tracked, momentum, eps,
                                                        scale, shift, mean, invstd);
   if (int rc = check_launch("pn2_bn_finalize")) return rc;
@@ -401,7 +421,7 @@ PN2_EXPORT int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, doubl
                                    float *ca, float *cb, float *cc, float *dgamma, float *dbeta, void *stream) {
   PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && count > 0.0,
               "pn2_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(np + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_bwd_finalize_kernel<<<(np + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, static_cast<cudaStream_t>(stream)>>>(
       training, tiles, c, np, count, stats, sums, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
   return check_launch("pn2_bn_bwd_finalize");
 }

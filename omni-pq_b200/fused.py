@@ -105,6 +105,16 @@ def _sync_group(bn):
     return group if dist.get_world_size(group) > 1 else None
 
 
+def all_reduce_stats(sums, count, group):
+    """SyncBatchNorm exchange: `sums` = fp64 [2, C] per-rank totals (sum, sum of squares -- or, in the
+    backward, sum dz and sum dz*y), `count` = rows on this rank.  One all-reduce of 2C+1 doubles per
+    BatchNorm layer and direction (the reference's SyncBatchNorm issues an all_gather of 2C+1 floats in
+    the forward and an all_reduce of 2C in the backward).  Returns (sums, global count)."""
+    flat = torch.cat([sums.reshape(-1), torch.tensor([float(count)], dtype=torch.float64, device=sums.device)])
+    dist.all_reduce(flat, group=group)
+    return flat[:-1].view_as(sums), float(flat[-1].item())
+
+
 class _Layer:
     """Per-layer forward state kept for the backward pass."""
     __slots__ = ("cout", "cin", "kp", "np", "xyz_first", "feat_pad", "wt", "wp", "y", "scale", "shift", "mean",
@@ -119,11 +129,7 @@ def _bn_forward(L, bn, stats, tiles, rows):
     if training:
         pg = _sync_group(bn)
         if pg is not None:
-            sums = K.bn_reduce_stats(stats, tiles, L.cout, L.np)
-            cnt = torch.tensor([float(rows)], dtype=torch.float64, device=sums.device)
-            dist.all_reduce(sums, group=pg)
-            dist.all_reduce(cnt, group=pg)
-            count = float(cnt.item())
+            sums, count = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np), rows, pg)
             L.group = pg
         if count <= 1:
             raise ValueError("Expected more than 1 value per channel when training")
@@ -152,8 +158,7 @@ def _bn_backward(L, stats, tiles):
     """-> (ca, cb, cc, dgamma, dbeta) for dy = ca*dz + cb + cc*y."""
     sums = None
     if L.group is not None:
-        sums = K.bn_reduce_stats(stats, tiles, L.cout, L.np)
-        dist.all_reduce(sums, group=L.group)
+        sums, _ = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np), 0, L.group)
     return K.bn_bwd_finalize(L.training, tiles, L.cout, L.np, L.count, stats, sums, L.gamma.detach(), L.mean, L.invstd)
 
 
@@ -220,14 +225,19 @@ class _SAFunction(torch.autograd.Function):
         last = state[-1]
         out_pm, arg = K.bn_relu_pool(last.y, b * m, ns, last.cout, last.np, last.scale, last.shift)
         out = K.to_channel_major(out_pm, b, last.cout, m)
-        ctx.pn2 = (state, rows0, nrows, out_pm, arg, (b, n, m, ns, c_feat, ldf), inds)
+        # outputs go through save_for_backward (a plain attribute would tie output -> grad_fn -> ctx -> output
+        # into a reference cycle and the activations would only be freed by the cyclic GC)
+        rows0.keep = (feat_pm, idx, xyz_c)
+        ctx.save_for_backward(new_xyz, inds, out_pm)
+        ctx.pn2 = (state, rows0, nrows, arg, (b, n, m, ns, c_feat, ldf))
         ctx.mark_non_differentiable(inds, out_pm)
         ctx.set_materialize_grads(False)
         return new_xyz, out, inds, out_pm
 
     @staticmethod
     def backward(ctx, g_new_xyz, g_out, _g_inds, _g_pm):
-        state, rows0, nrows, out_pm, arg, (b, n, m, ns, c_feat, ldf), inds = ctx.pn2
+        state, rows0, nrows, arg, (b, n, m, ns, c_feat, ldf) = ctx.pn2
+        _new_xyz, inds, out_pm = ctx.saved_tensors
         need_xyz, need_feat = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         dev = out_pm.device
         dxyz = dfeat = None
@@ -287,14 +297,16 @@ class _FPFunction(torch.autograd.Function):
         last = state[-1]
         out_pm, _ = K.bn_relu_pool(last.y, nrows, 1, last.cout, last.np, last.scale, last.shift, want_arg=False)
         out = K.to_channel_major(out_pm, b, last.cout, n)
-        ctx.pn2 = (state, rows0, nrows, out_pm, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx))
+        ctx.save_for_backward(out_pm)
+        ctx.pn2 = (state, rows0, nrows, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx))
         ctx.mark_non_differentiable(out_pm)
         ctx.set_materialize_grads(False)
         return out, out_pm
 
     @staticmethod
     def backward(ctx, g_out, _g_pm):
-        state, rows0, nrows, out_pm, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx) = ctx.pn2
+        state, rows0, nrows, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx) = ctx.pn2
+        (out_pm,) = ctx.saved_tensors
         need_unknow, need_known = ctx.needs_input_grad[5], ctx.needs_input_grad[6]
         if g_out is None:
             return (None,) * (7 + 3 * len(state))
