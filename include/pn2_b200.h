@@ -137,11 +137,12 @@ typedef struct pn2_rows {
 int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, const float *w,
                          float *wt, float *wp, void *stream);
 
-/* y[rows][ldy] = A . wt   (A = `a` rows x kp, wt [kp][np]); also writes per-row-tile partial column sums
+/* y[rows][ldy] = A . W^T  (A = `a` rows x kp; wt [kp][np] and wp [np][kp] are the two prepared copies of W:
+ * the FFMA kernel reads wt, the tcgen05 kernel the K-major wp); also writes per-row-tile partial column sums
  * stats[tiles][2][np] (sum, sum of squares) for BatchNorm; returns the number of row tiles in *tiles.
- * `stats` may be NULL. */
-int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, float *y, int ldy, float *stats,
-                    int *tiles, void *stream);
+ * `stats` may be NULL.  PN2_TC=0 in the environment selects the FFMA kernel everywhere. */
+int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, const float *wp, float *y, int ldy,
+                    float *stats, int *tiles, void *stream);
 int pn2_mlp_tiles(int rows, int np); /* row tiles pn2_mlp_forward / pn2_mlp_dgrad use for this shape */
 
 /* BatchNorm statistics -> folded scale/shift (+ saved mean / invstd, running-stat update).
@@ -175,7 +176,8 @@ int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, co
                         const float *gamma, const float *mean, const float *invstd, float *ca, float *cb, float *cc,
                         float *dgamma, float *dbeta, void *stream);
 
-/* dX = dY . wp with dY given by `dy` (kind DY / DYPOOL), wp [kp_out=np of forward][kp].  Modes:
+/* dX = dY . W with dY given by `dy` (kind DY / DYPOOL); wp [np of forward][ldw] (FFMA kernel) and
+ * wt [kp][np of forward] (tcgen05 kernel, may be NULL) are the prepared copies of W.  Modes:
  *  PN2_DGRAD_MASK: dz_prev = dX * (prev_y*prev_scale+prev_shift > 0) stored to out[rows][ldo], partial
  *                  sums (dz_prev, dz_prev*prev_y) to stats;
  *  PN2_DGRAD_STORE: out = dX;
@@ -185,7 +187,7 @@ int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, co
 #define PN2_DGRAD_MASK 0
 #define PN2_DGRAD_STORE 1
 #define PN2_DGRAD_SCATTER 2
-int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, float *out, int ldo,
+int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, const float *wt, float *out, int ldo,
                   const float *prev_y, int ld_prev, const float *prev_scale, const float *prev_shift, float *stats,
                   int *tiles, const pn2_rows *gather, float *dfeat, int ldf, float *dxyz, const int *centre_src,
                   void *stream);

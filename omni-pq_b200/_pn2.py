@@ -329,7 +329,7 @@ _rp = ctypes.POINTER(Rows)
 _ip_ = ctypes.POINTER(ctypes.c_int)
 _d = ctypes.c_double
 _prep = _sig("pn2_mlp_prep_weights", _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
-_mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _i, _vp, _ip_, _vp)
+_mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _vp, _i, _vp, _ip_, _vp)
 _mlp_tiles = _sig("pn2_mlp_tiles", _i, _i, kernel=False)
 _bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _vp, _vp, _vp)
 _bn_fin = _sig("pn2_bn_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp)
@@ -339,7 +339,7 @@ _to_cm = _sig("pn2_to_channel_major", _i, _i, _i, _i, _vp, _vp, _vp)
 _pool_prep = _sig("pn2_pool_bwd_prep", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip_, _vp)
 _pool_tiles = _sig("pn2_pool_bwd_tiles", _i, kernel=False)
 _bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
-_dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
+_dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
 _wgrad = _sig("pn2_mlp_wgrad", _rp, _rp, _i, _i, _i, _i, _vp, _vp, _vp)
 lib.pn2_mlp_wgrad_workspace.argtypes = [_i, _i, _i]
 lib.pn2_mlp_wgrad_workspace.restype = ctypes.c_longlong
@@ -366,14 +366,14 @@ def mlp_prep_weights(w2d, xyz_first, feat_pad, kp, np_):
     return wt, wp
 
 
-def mlp_forward(rows, kp, np_, wt, want_stats=True):
+def mlp_forward(rows, kp, np_, wt, wp=None, want_stats=True):
     dev = wt.device
     y = _f32(dev, rows.rows, np_)
     tiles = _mlp_tiles(rows.rows, np_)
     stats = _f32(dev, max(tiles, 1), 2, np_) if want_stats else None
     t = ctypes.c_int(0)
     _annotate("gemm_kernel<forward>", flops=2.0 * rows.rows * kp * np_, nbytes=4.0 * rows.rows * (kp + np_))
-    _check(_mlp_fwd(ctypes.byref(rows), kp, np_, _ptr(wt), _ptr(y), np_, _p(stats), ctypes.byref(t), _stream()))
+    _check(_mlp_fwd(ctypes.byref(rows), kp, np_, _ptr(wt), _p(wp), _ptr(y), np_, _p(stats), ctypes.byref(t), _stream()))
     _launched()
     return y, stats, tiles
 
@@ -453,7 +453,7 @@ def bn_bwd_finalize(training, tiles, c, np_, count, stats, sums, gamma, mean, in
     return co[0], co[1], co[2], dg[0], dg[1]
 
 
-def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift):
+def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift, wt=None):
     """dz_prev [rows, ncols] and its BatchNorm-backward partial sums."""
     dev = wp.device
     out = _f32(dev, dy.rows, ncols)
@@ -461,17 +461,17 @@ def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift):
     stats = _f32(dev, max(tiles, 1), 2, ncols)
     t = ctypes.c_int(0)
     _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + 2 * ncols))
-    _check(_dgrad(DGRAD_MASK, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, _ptr(prev_y),
+    _check(_dgrad(DGRAD_MASK, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), _ptr(out), ncols, _ptr(prev_y),
                   prev_y.shape[1], _ptr(prev_scale), _ptr(prev_shift), _ptr(stats), ctypes.byref(t), None, None, 0,
                   None, None, _stream()))
     _launched()
     return out, stats, tiles
 
 
-def mlp_dgrad_store(dy, ncols, wp):
+def mlp_dgrad_store(dy, ncols, wp, wt=None):
     out = _f32(wp.device, dy.rows, ncols)
     _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
-    _check(_dgrad(DGRAD_STORE, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _ptr(out), ncols, None, 0, None, None,
+    _check(_dgrad(DGRAD_STORE, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), _ptr(out), ncols, None, 0, None, None,
                   None, None, None, None, 0, None, None, _stream()))
     _launched()
     return out
@@ -479,7 +479,7 @@ def mlp_dgrad_store(dy, ncols, wp):
 
 def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src):
     _annotate("gemm_kernel<dgrad+scatter>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
-    _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], None, 0, None, 0, None, None, None,
+    _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], None, None, 0, None, 0, None, None, None,
                   None, ctypes.byref(gather), _p(dfeat), dfeat.shape[1] if dfeat is not None else 0, _p(dxyz),
                   _p(centre_src), _stream()))
     _launched()

@@ -15,106 +15,12 @@
 // (256 threads, 8x8 register micro-tile, double-buffered shared memory, 128-bit loads everywhere) or
 // 64x64x16 when the problem would leave SMs idle; weight-gradient launches split the position
 // dimension across CTAs and reduce the partial tiles in a fixed order.
-#include "pn2_common.cuh"
+#include "mlp_rows.cuh"
 
 namespace pn2 {
 namespace {
 
 constexpr int BK = 16;
-
-__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-
-// ---- row sources ------------------------------------------------------------------------------------
-struct RowCtx {
-  bool valid;
-  size_t off;   // element offset of the row in x (PLAIN/BNRELU/DY*: row*ld; GATHER: src*ld)
-  size_t goff;  // DYPOOL: g*ld; GATHER: source row (cloud*n_src + idx)
-  int slot;     // DYPOOL: row % group
-  float gx, gy, gz;  // GATHER: local coordinates
-};
-
-template <int KIND>
-__device__ __forceinline__ RowCtx row_ctx(const pn2_rows &s, int row) {
-  RowCtx c;
-  c.valid = row < s.rows;
-  c.off = 0; c.goff = 0; c.slot = 0; c.gx = c.gy = c.gz = 0.f;
-  if (!c.valid) return c;
-  if (KIND == PN2_ROWS_GATHER) {
-    const int cloud = row / (s.npoint * s.nsample);
-    const int centre = row / s.nsample;
-    const size_t src = static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row);
-    c.off = src * s.ld;
-    c.goff = src;
-    if (s.use_xyz) {
-      const float *p = s.xyz + src * 3, *q = s.centres + static_cast<size_t>(centre) * 3;
-      // pointnet2_utils.py:350-352: grouped_xyz -= new_xyz; grouped_xyz /= radius
-      c.gx = __fdiv_rn(__fsub_rn(__ldg(p + 0), __ldg(q + 0)), s.inv_scale);
-      c.gy = __fdiv_rn(__fsub_rn(__ldg(p + 1), __ldg(q + 1)), s.inv_scale);
-      c.gz = __fdiv_rn(__fsub_rn(__ldg(p + 2), __ldg(q + 2)), s.inv_scale);
-    }
-  } else {
-    c.off = static_cast<size_t>(row) * s.ld;
-    if (KIND == PN2_ROWS_DYPOOL) {
-      const int g = row / s.group;
-      c.goff = static_cast<size_t>(g) * s.ld;
-      c.slot = row - g * s.group;
-    }
-  }
-  return c;
-}
-
-template <int KIND>
-__device__ __forceinline__ float4 load4(const pn2_rows &s, const RowCtx &c, int c4) {
-  if (!c.valid || c4 >= s.cols) return zero4();
-  if (KIND == PN2_ROWS_PLAIN) return ldg4(s.x + c.off + c4);
-  if (KIND == PN2_ROWS_BNRELU) {
-    const float4 v = ldg4(s.x + c.off + c4), a = ldg4(s.c0 + c4), b = ldg4(s.c1 + c4);
-    return make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f),
-                       fmaxf(fmaf(v.z, a.z, b.z), 0.f), fmaxf(fmaf(v.w, a.w, b.w), 0.f));
-  }
-  if (KIND == PN2_ROWS_GATHER) {
-    if (c4 < s.feat_cols) return ldg4(s.x + c.off + c4);
-    return make_float4(c.gx, c.gy, c.gz, 0.f);  // c4 == feat_cols: the xyz block
-  }
-  // DY / DYPOOL: dy = c0*dz + c1 + c2*y
-  const float4 y = ldg4(s.x + c.off + c4);
-  const float4 ca = ldg4(s.c0 + c4), cb = ldg4(s.c1 + c4), cc = ldg4(s.c2 + c4);
-  float4 dz;
-  if (KIND == PN2_ROWS_DY) {
-    dz = ldg4(s.dz + c.off + c4);
-  } else {
-    const float4 g = ldg4(s.dz + c.goff + c4);
-    const uchar4 a = __ldg(reinterpret_cast<const uchar4 *>(s.arg + c.goff + c4));
-    dz = make_float4(a.x == c.slot ? g.x : 0.f, a.y == c.slot ? g.y : 0.f, a.z == c.slot ? g.z : 0.f,
-                     a.w == c.slot ? g.w : 0.f);
-  }
-  return make_float4(fmaf(cc.x, y.x, fmaf(ca.x, dz.x, cb.x)), fmaf(cc.y, y.y, fmaf(ca.y, dz.y, cb.y)),
-                     fmaf(cc.z, y.z, fmaf(ca.z, dz.z, cb.z)), fmaf(cc.w, y.w, fmaf(ca.w, dz.w, cb.w)));
-}
-
-// ---- epilogues ----------------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_STORE_STATS = 1, EPI_DGRAD_MASK = 2, EPI_SCATTER = 3 };
-
-struct GemmArgs {
-  pn2_rows A, B;
-  int M, N, K;          // logical extents (all multiples of 4 where they index channels)
-  int k_per_split;      // multiple of BK; blockIdx.z selects the split
-  float *out;           // [M][ldo] (+ blockIdx.z * out_split_stride)
-  int ldo;
-  long long out_split_stride;
-  float *stats;         // [gridDim.x][2][stats_ld]
-  int stats_ld;
-  // EPI_DGRAD_MASK
-  const float *prev_y, *prev_scale, *prev_shift;
-  int ld_prev;
-  // EPI_SCATTER
-  pn2_rows G;           // the forward's gather source
-  float *dfeat;
-  int ldf;
-  float *dxyz;
-  const int *centre_src;
-};
 
 template <int BM, int BN, int AKIND, bool ATRANS, int BKIND, int EPI>
 __global__ void __launch_bounds__((BM / 8) * (BN / 8), (BM == 128 ? 2 : 6))
@@ -414,11 +320,12 @@ PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_p
 }
 
 PN2_EXPORT int pn2_mlp_tiles(int rows, int ncols) {
+  if (gemm_tc_enabled()) return (rows + 127) / 128;  // the tcgen05 kernel always tiles rows by 128
   return big_tile(rows, ncols) ? (rows + 127) / 128 : (rows + 63) / 64;
 }
 
-PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, float *y, int ldy, float *stats,
-                               int *tiles, void *stream_) {
+PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, const float *wp, float *y,
+                               int ldy, float *stats, int *tiles, void *stream_) {
   if (int rc = check_rows(a, "pn2_mlp_forward")) return rc;
   PN2_REQUIRE(a->cols == kp && (np % 4) == 0 && np > 0 && wt && y && ldy >= np && (ldy % 4) == 0,
               "pn2_mlp_forward: operand widths disagree (a.cols=%d kp=%d np=%d ldy=%d)", a->cols, kp, np, ldy);
@@ -434,6 +341,13 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
   g.out = y; g.ldo = ldy;
   g.stats = stats; g.stats_ld = np;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (wp != nullptr && gemm_tc_enabled()) {  // tensor-core path: B = W as [np][kp], K-major
+    GemmArgs t = g;
+    t.B = plain_rows(wp, np, kp, kp);
+    const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
+    if (rc != PN2_TC_UNSUPPORTED) return rc;
+  }
+  PN2_REQUIRE(!gemm_tc_enabled(), "pn2_mlp_forward: tensor-core path unavailable for this call (wp missing?)");
   switch (a->kind) {
     case PN2_ROWS_PLAIN: return launch_gemm<PN2_ROWS_PLAIN, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
     case PN2_ROWS_BNRELU: return launch_gemm<PN2_ROWS_BNRELU, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
@@ -441,7 +355,8 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
   }
 }
 
-PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, float *out, int ldo,
+PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const float *wp, int ldw, const float *wt,
+                             float *out, int ldo,
                              const float *prev_y, int ld_prev, const float *prev_scale, const float *prev_shift,
                              float *stats, int *tiles, const pn2_rows *gather, float *dfeat, int ldf, float *dxyz,
                              const int *centre_src, void *stream_) {
@@ -459,14 +374,29 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
   g.stats = stats; g.stats_ld = ncols;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const bool pool = dy->kind == PN2_ROWS_DYPOOL;
+  const bool tc = wt != nullptr && gemm_tc_enabled() && mode != PN2_DGRAD_SCATTER;
+  PN2_REQUIRE(tc || !gemm_tc_enabled() || mode == PN2_DGRAD_SCATTER, "pn2_mlp_dgrad: tensor-core path needs wt");
+  GemmArgs t;
   if (mode == PN2_DGRAD_MASK) {
     PN2_REQUIRE(out && prev_y && prev_scale && prev_shift && ldo >= ncols && ld_prev >= ncols, "pn2_mlp_dgrad: MASK needs out/prev_*");
     g.prev_y = prev_y; g.prev_scale = prev_scale; g.prev_shift = prev_shift; g.ld_prev = ld_prev;
+    if (tc) {  // B = W^T as [ncols][dy.cols], K-major: that is wt
+      t = g;
+      t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+      const int rc = gemm_tc_launch(dy->kind, EPI_DGRAD_MASK, &t, s);
+      if (rc != PN2_TC_UNSUPPORTED) return rc;
+    }
     return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_DGRAD_MASK>(g, 1, s, "pn2_mlp_dgrad")
                 : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_DGRAD_MASK>(g, 1, s, "pn2_mlp_dgrad");
   }
   if (mode == PN2_DGRAD_STORE) {
     PN2_REQUIRE(out && ldo >= ncols, "pn2_mlp_dgrad: STORE needs out");
+    if (tc) {
+      t = g;
+      t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+      const int rc = gemm_tc_launch(dy->kind, EPI_STORE, &t, s);
+      if (rc != PN2_TC_UNSUPPORTED) return rc;
+    }
     return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_STORE>(g, 1, s, "pn2_mlp_dgrad")
                 : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_STORE>(g, 1, s, "pn2_mlp_dgrad");
   }

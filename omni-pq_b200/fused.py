@@ -147,7 +147,7 @@ def _run_mlp(layers, rows0, nrows, xyz_first, feat_pad, need_grad):
         L.kp, L.np = kp, pad4(L.cout)
         L.xyz_first, L.feat_pad = (xyz_first, feat_pad) if li == 0 else (0, 0)
         L.wt, L.wp = K.mlp_prep_weights(conv.weight.detach().view(L.cout, L.cin), L.xyz_first, L.feat_pad, L.kp, L.np)
-        L.y, stats, tiles = K.mlp_forward(src, L.kp, L.np, L.wt, want_stats=bn.training)
+        L.y, stats, tiles = K.mlp_forward(src, L.kp, L.np, L.wt, L.wp, want_stats=bn.training)
         _bn_forward(L, bn, stats, tiles, nrows)
         state.append(L)
         src, kp = K.rows_bnrelu(L.y, nrows, L.np, L.np, L.scale, L.shift), L.np
@@ -182,7 +182,7 @@ def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
         dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device)
         grads[li] = (dw.view(L.cout, L.cin, 1, 1), dgamma, dbeta)
         if li > 0:
-            dz, stats, tiles = K.mlp_dgrad_mask(dy, P.np, L.wp, P.y, P.scale, P.shift)
+            dz, stats, tiles = K.mlp_dgrad_mask(dy, P.np, L.wp, P.y, P.scale, P.shift, wt=L.wt)
             ca, cb, cc, dgamma, dbeta = _bn_backward(P, stats, tiles)
             dy = K.rows_dy(P.y, dz, nrows, P.np, P.np, ca, cb, cc)
         else:
@@ -316,7 +316,7 @@ class _FPFunction(torch.autograd.Function):
 
         def first_dgrad(dy, L0):
             if need_unknow or need_known:
-                box["dx"] = K.mlp_dgrad_store(dy, ldx, L0.wp)
+                box["dx"] = K.mlp_dgrad_store(dy, ldx, L0.wp, wt=L0.wt)
 
         per_layer = _mlp_backward(state, rows0, nrows, gz, out_pm, None, 1, first_dgrad)
         grads = [g for triple in per_layer for g in triple]
