@@ -477,9 +477,9 @@ def mlp_dgrad_store(dy, ncols, wp, wt=None):
     return out
 
 
-def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src):
+def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src, wt=None):
     _annotate("gemm_kernel<dgrad+scatter>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
-    _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], None, None, 0, None, 0, None, None, None,
+    _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), None, 0, None, 0, None, None, None,
                   None, ctypes.byref(gather), _p(dfeat), dfeat.shape[1] if dfeat is not None else 0, _p(dxyz),
                   _p(centre_src), _stream()))
     _launched()

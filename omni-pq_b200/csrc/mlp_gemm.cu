@@ -214,7 +214,9 @@ inline bool big_tile(long long m, long long n) {
 
 template <int AKIND, bool ATRANS, int BKIND, int EPI>
 int launch_gemm(const GemmArgs &g, int splits, cudaStream_t stream, const char *what) {
-  if (big_tile(g.M, g.N)) {
+  // while the tcgen05 path is enabled the statistics buffers are sized for 128-row tiles (pn2_mlp_tiles), so a
+  // call that falls back to this kernel (K beyond the tensor-core kernel's coefficient staging) keeps that tiling
+  if (big_tile(g.M, g.N) || (gemm_tc_enabled() && g.stats != nullptr)) {
     dim3 grid((g.M + 127) / 128, (g.N + 127) / 128, splits);
     gemm_kernel<128, 128, AKIND, ATRANS, BKIND, EPI><<<grid, 256, 0, stream>>>(g);
   } else {
@@ -292,6 +294,15 @@ __global__ void wgrad_reduce_kernel(int cout, int cin, int xyz_first, int feat_p
 }
 
 int wgrad_splits(int rows, int np, int kp) {
+  if (gemm_tc_enabled()) {  // tcgen05 kernel: 128x128 tiles, 1 CTA/SM, position slices of >= 4 k-blocks of 32
+    const long long t = ((np + 127) / 128) * ((kp + 127) / 128);
+    long long s = (static_cast<long long>(sm_count()) + t - 1) / t;
+    const long long cap = (rows + 127) / 128;
+    if (s > cap) s = cap;
+    if (s < 1) s = 1;
+    if (s > 512) s = 512;
+    return static_cast<int>(s);
+  }
   const long long tiles = big_tile(np, kp) ? ((np + 127) / 128) * ((kp + 127) / 128) : ((np + 63) / 64) * ((kp + 63) / 64);
   const int per_sm = big_tile(np, kp) ? 2 : 6;
   long long s = (static_cast<long long>(sm_count()) * per_sm + tiles - 1) / tiles;
@@ -347,7 +358,6 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
     const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
-  PN2_REQUIRE(!gemm_tc_enabled(), "pn2_mlp_forward: tensor-core path unavailable for this call (wp missing?)");
   switch (a->kind) {
     case PN2_ROWS_PLAIN: return launch_gemm<PN2_ROWS_PLAIN, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
     case PN2_ROWS_BNRELU: return launch_gemm<PN2_ROWS_BNRELU, true, PN2_ROWS_PLAIN, EPI_STORE_STATS>(g, 1, s, "pn2_mlp_forward");
@@ -375,7 +385,6 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const bool pool = dy->kind == PN2_ROWS_DYPOOL;
   const bool tc = wt != nullptr && gemm_tc_enabled() && mode != PN2_DGRAD_SCATTER;
-  PN2_REQUIRE(tc || !gemm_tc_enabled() || mode == PN2_DGRAD_SCATTER, "pn2_mlp_dgrad: tensor-core path needs wt");
   GemmArgs t;
   if (mode == PN2_DGRAD_MASK) {
     PN2_REQUIRE(out && prev_y && prev_scale && prev_shift && ldo >= ncols && ld_prev >= ncols, "pn2_mlp_dgrad: MASK needs out/prev_*");
@@ -408,6 +417,12 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
   PN2_REQUIRE((dfeat == nullptr || ldf >= gather->feat_cols) && (dxyz == nullptr || centre_src != nullptr),
               "pn2_mlp_dgrad: SCATTER targets inconsistent");
   g.G = *gather; g.dfeat = dfeat; g.ldf = ldf; g.dxyz = dxyz; g.centre_src = centre_src;
+  if (wt != nullptr && gemm_tc_enabled()) {
+    GemmArgs t2 = g;
+    t2.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+    const int rc = gemm_tc_launch(dy->kind, EPI_SCATTER, &t2, s);
+    if (rc != PN2_TC_UNSUPPORTED) return rc;
+  }
   return pool ? launch_gemm<PN2_ROWS_DYPOOL, true, PN2_ROWS_PLAIN, EPI_SCATTER>(g, 1, s, "pn2_mlp_dgrad")
               : launch_gemm<PN2_ROWS_DY, true, PN2_ROWS_PLAIN, EPI_SCATTER>(g, 1, s, "pn2_mlp_dgrad");
 }
@@ -430,10 +445,14 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   GemmArgs g = {};
   g.A = *dy; g.B = *a;
   g.M = np; g.N = kp; g.K = rows;
-  g.k_per_split = ((rows + splits - 1) / splits + BK - 1) / BK * BK;
+  g.k_per_split = ((rows + splits - 1) / splits + 31) / 32 * 32;  // multiple of both kernels' k-block
   g.out = ws; g.ldo = kp; g.out_split_stride = static_cast<long long>(np) * kp;
-  int rc = PN2_OK;
-  if (rows > 0) {
+  int rc = PN2_TC_UNSUPPORTED;
+  if (rows > 0 && gemm_tc_enabled()) {
+    rc = gemm_tc_wgrad_launch(&g, splits, s);
+    if (rc != PN2_TC_UNSUPPORTED && rc != PN2_OK) return rc;
+  }
+  if (rows > 0 && rc == PN2_TC_UNSUPPORTED) {
 #define PN2_WGRAD(DK, AK) launch_gemm<DK, false, AK, EPI_STORE>(g, splits, s, "pn2_mlp_wgrad")
     const bool pool = dy->kind == PN2_ROWS_DYPOOL;
     switch (a->kind) {

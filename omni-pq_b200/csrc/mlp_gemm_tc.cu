@@ -31,10 +31,74 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/;
+constexpr int TC_KMAX = 1152;                        // largest K of the non-transposed form (coefficient staging)
+constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over K (or over 128 tile channels); B: 2 x 128
+constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
 constexpr uint32_t TMEM_COLS = 128;
 
-enum { TC_EPI_STORE = 0, TC_EPI_STORE_STATS = 1, TC_EPI_DGRAD_MASK = 2 };
+enum { TC_EPI_STORE = 0, TC_EPI_STORE_STATS = 1, TC_EPI_DGRAD_MASK = 2, TC_EPI_SCATTER = 3 };
+
+
+// ---- two-phase row sources: issue the global loads of the NEXT k-block (fetch), run the element-wise
+// transform of the CURRENT one (apply) with per-channel coefficients taken from shared memory, so a warp
+// never stalls on a load it has just issued -------------------------------------------------------------
+struct Raw {
+  float4 x;   // matrix value (PLAIN / BNRELU / GATHER features / DY*: pre-BN y)
+  float4 d;   // DY: dz; DYPOOL: pooled gz
+  uchar4 a;   // DYPOOL: arg-max slot
+};
+
+template <int KIND>
+__device__ __forceinline__ Raw fetch_raw(const pn2_rows &s, const RowCtx &c, int c4) {
+  Raw r;
+  r.x = zero4(); r.d = zero4(); r.a = make_uchar4(0, 0, 0, 0);
+  if (!c.valid || c4 >= s.cols) return r;
+  if (KIND == PN2_ROWS_GATHER) {
+    if (c4 < s.feat_cols) r.x = ldg4(s.x + c.off + c4);
+    return r;
+  }
+  r.x = ldg4(s.x + c.off + c4);
+  if (KIND == PN2_ROWS_DY) r.d = ldg4(s.dz + c.off + c4);
+  if (KIND == PN2_ROWS_DYPOOL) {
+    r.d = ldg4(s.dz + c.goff + c4);
+    r.a = __ldg(reinterpret_cast<const uchar4 *>(s.arg + c.goff + c4));
+  }
+  return r;
+}
+
+// coef: shared-memory copies of the source's per-channel vectors c0,c1,c2, indexed by (c4 - coef_base)
+template <int KIND>
+__device__ __forceinline__ float4 apply_raw(const pn2_rows &s, const RowCtx &c, int c4, const Raw &r,
+                                            const float *coef, int coef_ld, int coef_base) {
+  if (!c.valid || c4 >= s.cols) return zero4();
+  if (KIND == PN2_ROWS_PLAIN) return r.x;
+  if (KIND == PN2_ROWS_GATHER) return c4 < s.feat_cols ? r.x : make_float4(c.gx, c.gy, c.gz, 0.f);
+  const int ci = c4 - coef_base;
+  const float4 k0 = *reinterpret_cast<const float4 *>(coef + ci);
+  const float4 k1 = *reinterpret_cast<const float4 *>(coef + coef_ld + ci);
+  if (KIND == PN2_ROWS_BNRELU)
+    return make_float4(fmaxf(fmaf(r.x.x, k0.x, k1.x), 0.f), fmaxf(fmaf(r.x.y, k0.y, k1.y), 0.f),
+                       fmaxf(fmaf(r.x.z, k0.z, k1.z), 0.f), fmaxf(fmaf(r.x.w, k0.w, k1.w), 0.f));
+  const float4 k2 = *reinterpret_cast<const float4 *>(coef + 2 * coef_ld + ci);
+  float4 dz = r.d;
+  if (KIND == PN2_ROWS_DYPOOL)
+    dz = make_float4(r.a.x == c.slot ? dz.x : 0.f, r.a.y == c.slot ? dz.y : 0.f, r.a.z == c.slot ? dz.z : 0.f,
+                     r.a.w == c.slot ? dz.w : 0.f);
+  return make_float4(fmaf(k2.x, r.x.x, fmaf(k0.x, dz.x, k1.x)), fmaf(k2.y, r.x.y, fmaf(k0.y, dz.y, k1.y)),
+                     fmaf(k2.z, r.x.z, fmaf(k0.z, dz.z, k1.z)), fmaf(k2.w, r.x.w, fmaf(k0.w, dz.w, k1.w)));
+}
+
+template <int KIND>
+__device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int coef_ld, int base, int count, int tid) {
+  if (KIND == PN2_ROWS_PLAIN || KIND == PN2_ROWS_GATHER) return;
+  for (int i = tid; i < count; i += TC_THREADS) {
+    const int c = base + i;
+    const bool ok = c < s.cols;
+    coef[i] = ok ? __ldg(s.c0 + c) : 0.f;
+    coef[coef_ld + i] = ok ? __ldg(s.c1 + c) : 0.f;
+    if (KIND == PN2_ROWS_DY || KIND == PN2_ROWS_DYPOOL) coef[2 * coef_ld + i] = ok ? __ldg(s.c2 + c) : 0.f;
+  }
+}
 
 // column totals over the 32 lanes of a warp: afterwards lane l holds the sum of v[l] over all lanes
 __device__ __forceinline__ float warp_column_sum(float (&v)[32], int lane) {
@@ -51,7 +115,12 @@ __device__ __forceinline__ float warp_column_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int AKIND, int EPI>
+// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory.
+// TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and B = activation source are both
+// position rows with channels contiguous, so a k-block is staged transposed (lane = position, 4-byte stores,
+// conflict-free because the 32 lanes of a warp fill one 128-byte swizzle row); blockIdx.z selects a slice of
+// positions and the partial tile goes to out + blockIdx.z * out_split_stride.
+template <int AKIND, int BKIND, bool TRANS, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
@@ -59,6 +128,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + TC_STAGES * STAGE_BYTES);  // [TC_STAGES]
   uint64_t *done_bar = empty_bar + TC_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  float *coef_a = reinterpret_cast<float *>(tiles + TC_STAGES * STAGE_BYTES + 256);  // [3][coef_ld_a]
+  float *coef_b = coef_a + 3 * TC_KMAX;                                              // [2][128]
   __shared__ float red[2][8][32];  // per-warp column partials for the statistics epilogues
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,40 +146,104 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
 
-  // producer mapping: thread -> one tile row (A: a position, B: an output channel) and 4 of its 8 chunks
+  const uint32_t idesc = idesc_tf32(TM, TN);
+  const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
+  const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
+  const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
+
+  // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
+  // tile's 128 output rows / columns for the transposed form)
+  const int coef_ld_a = TRANS ? 128 : TC_KMAX;
+  const int coef_base_a = TRANS ? m0 : 0, coef_base_b = TRANS ? n0 : 0;
+  stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
+  if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
+  __syncthreads();
+
+  // producer mapping, plain form: thread -> one tile row (A: a position, B: an output channel) and 4 of its 8
+  // 16-byte chunks; transposed form: lane -> position inside the k-block, warp -> 16 channels of each operand
   const int prow = tid & (TM - 1);
   const int chunk0 = (tid >> 7) * 4;
-  const RowCtx actx = row_ctx<AKIND>(g.A, m0 + prow);
-  const RowCtx bctx = row_ctx<PN2_ROWS_PLAIN>(g.B, n0 + prow);
+  const int tch = warp * 16;
+  const uint32_t toff = static_cast<uint32_t>(((lane >> 2) << 4) | ((lane & 3) << 2));
   uint32_t off[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) off[i] = sw128_offset(prow, chunk0 + i);
 
-  const uint32_t idesc = idesc_tf32(TM, TN);
-  const int num_kb = (g.K + TK - 1) / TK;
+  RowCtx ca, cb, ca_next, cb_next;
+  auto make_ctx = [&](int kb, RowCtx &xa, RowCtx &xb) {
+    if (!TRANS) return;
+    const int p = k_begin + kb * TK + lane;
+    const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
+    xa = row_ctx<AKIND>(g.A, r);
+    xb = row_ctx<BKIND>(g.B, r);
+  };
+  if (TRANS) {
+    make_ctx(0, ca, cb);
+    make_ctx(1, ca_next, cb_next);
+  } else {
+    ca = row_ctx<AKIND>(g.A, m0 + prow);
+    cb = row_ctx<BKIND>(g.B, n0 + prow);
+  }
+  auto col_a = [&](int kb, int i) { return TRANS ? m0 + tch + i * 4 : k_begin + kb * TK + (chunk0 + i) * 4; };
+  auto col_b = [&](int kb, int i) { return TRANS ? n0 + tch + i * 4 : k_begin + kb * TK + (chunk0 + i) * 4; };
+
+  Raw ra[4], rb[4], ra_next[4], rb_next[4];
+  if (num_kb > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = fetch_raw<AKIND>(g.A, ca, col_a(0, i));
+      rb[i] = fetch_raw<BKIND>(g.B, cb, col_b(0, i));
+    }
+  }
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
-    if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);  // MMAs of block kb-STAGES done
-    unsigned char *st = tiles + s * STAGE_BYTES;
-    const int k0 = kb * TK;
-    float4 va[4], vb[4];
+    // 1. put the next k-block's loads in flight (transposed form: with the row contexts resolved one block ago)
+    if (kb + 1 < num_kb) {
+      const RowCtx &na = TRANS ? ca_next : ca;
+      const RowCtx &nb = TRANS ? cb_next : cb;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      va[i] = load4<AKIND>(g.A, actx, k0 + (chunk0 + i) * 4);
-      vb[i] = load4<PN2_ROWS_PLAIN>(g.B, bctx, k0 + (chunk0 + i) * 4);
+      for (int i = 0; i < 4; ++i) {
+        ra_next[i] = fetch_raw<AKIND>(g.A, na, col_a(kb + 1, i));
+        rb_next[i] = fetch_raw<BKIND>(g.B, nb, col_b(kb + 1, i));
+      }
     }
+    RowCtx ca_nn, cb_nn;
+    make_ctx(kb + 2, ca_nn, cb_nn);
+    // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
+    if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
+    unsigned char *st = tiles + s * STAGE_BYTES;
+    // 3. transform + split + store the current block
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 hi, lo;
-      split_tf32(va[i].x, hi.x, lo.x); split_tf32(va[i].y, hi.y, lo.y);
-      split_tf32(va[i].z, hi.z, lo.z); split_tf32(va[i].w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-      *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-      split_tf32(vb[i].x, hi.x, lo.x); split_tf32(vb[i].y, hi.y, lo.y);
-      split_tf32(vb[i].z, hi.z, lo.z); split_tf32(vb[i].w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-      *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
+      const float4 va = apply_raw<AKIND>(g.A, ca, col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
+      const float4 vb = apply_raw<BKIND>(g.B, cb, col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
+      if (!TRANS) {
+        float4 hi, lo;
+        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
+        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
+        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
+        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
+      } else {
+        const float a4[4] = {va.x, va.y, va.z, va.w};
+        const float b4[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = tch + i * 4 + e;  // tile row = channel
+          const uint32_t o = static_cast<uint32_t>((c >> 3) * 1024 + (c & 7) * 128) + (toff ^ static_cast<uint32_t>((c & 7) << 4));
+          float hi, lo;
+          split_tf32(a4[e], hi, lo);
+          *reinterpret_cast<float *>(st + 0 * TILE_BYTES + o) = hi;
+          *reinterpret_cast<float *>(st + 1 * TILE_BYTES + o) = lo;
+          split_tf32(b4[e], hi, lo);
+          *reinterpret_cast<float *>(st + 2 * TILE_BYTES + o) = hi;
+          *reinterpret_cast<float *>(st + 3 * TILE_BYTES + o) = lo;
+        }
+      }
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -127,8 +262,18 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       mma_commit(&empty_bar[s]);
       if (kb == num_kb - 1) mma_commit(done_bar);
     }
+    // 4. rotate the prefetch registers
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = ra_next[i];
+      rb[i] = rb_next[i];
+    }
+    if (TRANS) {
+      ca = ca_next; cb = cb_next;
+      ca_next = ca_nn; cb_next = cb_nn;
+    }
   }
-  mbar_wait(done_bar, 0);
+  if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
 
   // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (rows), warps 0-3 columns 0-63, warps 4-7 columns 64-127
@@ -140,7 +285,12 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     const int c_local = cbase + cc * 32;
     const int col = n0 + c_local;
     float v[32];
-    tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+    if (num_kb > 0) {
+      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+    } else {  // empty position slice of a split weight gradient: the accumulator was never written
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
     float q[32];  // second statistic operand
     if (EPI == TC_EPI_DGRAD_MASK) {
 #pragma unroll
@@ -161,13 +311,30 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
     }
-    if (row_ok) {
-      float *dst = g.out + static_cast<size_t>(row) * g.ldo + col;
+    if (EPI == TC_EPI_SCATTER) {
+      if (row_ok) {  // transpose of the gather: scatter-add into the neighbour's feature row / coordinates
+        const RowCtx gc = row_ctx<PN2_ROWS_GATHER>(g.G, row);
+        const int fc = g.G.feat_cols;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = col + j;
+          if (c < fc) {
+            if (g.dfeat) atomicAdd(g.dfeat + gc.goff * g.ldf + c, v[j]);
+          } else if (c < fc + 3 && g.dxyz && g.G.use_xyz) {
+            const float gv = __fdiv_rn(v[j], g.G.inv_scale);
+            atomicAdd(g.dxyz + gc.goff * 3 + (c - fc), gv);
+            const int centre = row / g.G.nsample, cloud = row / (g.G.npoint * g.G.nsample);
+            atomicAdd(g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3 + (c - fc), -gv);
+          }
+        }
+      }
+    } else if (row_ok) {
+      float *dst = g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         if (col + j < g.N) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    if (EPI != TC_EPI_STORE && g.stats != nullptr) {
+    if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
       // rows beyond M hold exact zeros (their A rows were zero), so they do not disturb the sums
       const float s1 = warp_column_sum(v, lane);
       const float s2 = warp_column_sum(q, lane);
@@ -194,9 +361,9 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
-template <int AKIND, int EPI>
-int launch_tc(const GemmArgs &g, cudaStream_t stream) {
-  auto kernel = gemm_tc_kernel<AKIND, EPI>;
+template <int AKIND, int BKIND, bool TRANS, int EPI>
+int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
+  auto kernel = gemm_tc_kernel<AKIND, BKIND, TRANS, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -204,7 +371,7 @@ int launch_tc(const GemmArgs &g, cudaStream_t stream) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     configured_dev = dev;
   }
-  dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN);
+  dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, splits);
   kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(g);
   return check_launch("gemm_tc_kernel");
 }
@@ -220,13 +387,13 @@ bool gemm_tc_enabled() {
   return on == 1;
 }
 
-// epi uses mlp_gemm.cu's numbering: 0 store, 1 store+stats, 2 dgrad mask.  Tiles follow mlp_gemm.cu's
-// 128-row tiling, so the statistics buffer sized by pn2_mlp_tiles() fits.
+// epi uses mlp_gemm.cu's numbering: 0 store, 1 store+stats, 2 dgrad mask, 3 scatter.  Row tiles are always 128
+// rows, which is what pn2_mlp_tiles() reports while this path is enabled.
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
-  if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || epi > 2) return PN2_TC_UNSUPPORTED;
+  if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
 #define PN2_TC_CASE(AK, EP) \
-  if (akind == AK && epi == EP) return launch_tc<AK, EP>(g, stream);
+  if (akind == AK && epi == EP) return launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)
@@ -234,7 +401,26 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
   PN2_TC_CASE(PN2_ROWS_DYPOOL, TC_EPI_DGRAD_MASK)
   PN2_TC_CASE(PN2_ROWS_DY, TC_EPI_STORE)
   PN2_TC_CASE(PN2_ROWS_DYPOOL, TC_EPI_STORE)
+  PN2_TC_CASE(PN2_ROWS_DY, TC_EPI_SCATTER)
+  PN2_TC_CASE(PN2_ROWS_DYPOOL, TC_EPI_SCATTER)
 #undef PN2_TC_CASE
+  return PN2_TC_UNSUPPORTED;
+}
+
+// weight gradient: g.A = dY source, g.B = activation source, g.M = np, g.N = kp, g.K = positions,
+// g.k_per_split a multiple of 32, partial tiles to g.out + z * g.out_split_stride
+int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream) {
+  const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
+  if (!gemm_tc_enabled()) return PN2_TC_UNSUPPORTED;
+#define PN2_TC_W(AK, BK) \
+  if (g.A.kind == AK && g.B.kind == BK) return launch_tc<AK, BK, true, TC_EPI_STORE>(g, splits, stream);
+  PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_PLAIN)
+  PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_BNRELU)
+  PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_GATHER)
+  PN2_TC_W(PN2_ROWS_DYPOOL, PN2_ROWS_PLAIN)
+  PN2_TC_W(PN2_ROWS_DYPOOL, PN2_ROWS_BNRELU)
+  PN2_TC_W(PN2_ROWS_DYPOOL, PN2_ROWS_GATHER)
+#undef PN2_TC_W
   return PN2_TC_UNSUPPORTED;
 }
 

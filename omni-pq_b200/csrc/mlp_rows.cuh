@@ -104,6 +104,7 @@ struct GemmArgs {
 // tcgen05 path (mlp_gemm_tc.cu): returns PN2_TC_UNSUPPORTED when the shape / source / epilogue is not covered
 constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
+int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
 
 }  // namespace pn2

@@ -250,7 +250,7 @@ class _SAFunction(torch.autograd.Function):
 
             def first_dgrad(dy, L0):
                 if dfeat_pm is not None or dxyz_pm is not None:
-                    K.mlp_dgrad_scatter(dy, L0.kp, L0.wp, rows0, dfeat_pm, dxyz_pm, inds)
+                    K.mlp_dgrad_scatter(dy, L0.kp, L0.wp, rows0, dfeat_pm, dxyz_pm, inds, wt=L0.wt)
 
             per_layer = _mlp_backward(state, rows0, nrows, gz, out_pm, arg, ns, first_dgrad)
             grads = [g for triple in per_layer for g in triple]
