@@ -244,10 +244,14 @@ def main_ours(args):
             step_resident(it)
         torch.cuda.synchronize()
         recs = _pn2.profile_end()
-        agg = {}
+        agg, shapes = {}, {}
         for name, ms, flops, nbytes in recs:
-            a = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
+            base = name.split("[")[0]  # GEMM labels carry their shape: aggregate per kernel, keep the detail
+            a = agg.setdefault(base, [0.0, 0, 0.0, 0.0])
             a[0] += ms; a[1] += 1; a[2] += flops; a[3] += nbytes
+            if "[" in name:
+                d = shapes.setdefault(name, [0.0, 0, 0.0])
+                d[0] += ms; d[1] += 1; d[2] += flops
         total_ms = sum(a[0] for a in agg.values())
         kernels = []
         for name, (ms, cnt, flops, nbytes) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
@@ -258,6 +262,8 @@ def main_ours(args):
             if nbytes:
                 row["gbs"] = nbytes / (ms * 1e-3) / 1e9
             kernels.append(row)
+        gemm_shapes = [{"gemm": n, "us": 1e3 * ms / cnt, "tflops": fl / (ms * 1e-3) / 1e12 if ms else 0.0}
+                       for n, (ms, cnt, fl) in sorted(shapes.items(), key=lambda kv: -kv[1][0])]
         top = kernels[0]
         if "tflops" in top:
             roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tflops"],
@@ -283,6 +289,7 @@ def main_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": args.batch * args.points * 6 * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "kernels": kernels,
+                "gemm_shapes": gemm_shapes,
                 "cpu_baseline": cpu_base}
         if not args.no_ref_gpu and world == 1:
             line["ref_gpu"] = ref_gpu_run(args, dev)

@@ -372,7 +372,7 @@ def mlp_forward(rows, kp, np_, wt, wp=None, want_stats=True):
     tiles = _mlp_tiles(rows.rows, np_)
     stats = _f32(dev, max(tiles, 1), 2, np_) if want_stats else None
     t = ctypes.c_int(0)
-    _annotate("gemm_kernel<forward>", flops=2.0 * rows.rows * kp * np_, nbytes=4.0 * rows.rows * (kp + np_))
+    _annotate(f"gemm_kernel<forward>[{rows.rows}x{kp}->{np_}]", flops=2.0 * rows.rows * kp * np_, nbytes=4.0 * rows.rows * (kp + np_))
     _check(_mlp_fwd(ctypes.byref(rows), kp, np_, _ptr(wt), _p(wp), _ptr(y), np_, _p(stats), ctypes.byref(t), _stream()))
     _launched()
     return y, stats, tiles
@@ -460,7 +460,7 @@ def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift, wt=None):
     tiles = _mlp_tiles(dy.rows, ncols)
     stats = _f32(dev, max(tiles, 1), 2, ncols)
     t = ctypes.c_int(0)
-    _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + 2 * ncols))
+    _annotate(f"gemm_kernel<dgrad>[{dy.rows}x{dy.cols}->{ncols}]", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + 2 * ncols))
     _check(_dgrad(DGRAD_MASK, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), _ptr(out), ncols, _ptr(prev_y),
                   prev_y.shape[1], _ptr(prev_scale), _ptr(prev_shift), _ptr(stats), ctypes.byref(t), None, None, 0,
                   None, None, _stream()))
@@ -470,7 +470,7 @@ def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift, wt=None):
 
 def mlp_dgrad_store(dy, ncols, wp, wt=None):
     out = _f32(wp.device, dy.rows, ncols)
-    _annotate("gemm_kernel<dgrad>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
+    _annotate(f"gemm_kernel<dgrad>[{dy.rows}x{dy.cols}->{ncols}]", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
     _check(_dgrad(DGRAD_STORE, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), _ptr(out), ncols, None, 0, None, None,
                   None, None, None, None, 0, None, None, _stream()))
     _launched()
@@ -478,7 +478,7 @@ def mlp_dgrad_store(dy, ncols, wp, wt=None):
 
 
 def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src, wt=None):
-    _annotate("gemm_kernel<dgrad+scatter>", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
+    _annotate(f"gemm_kernel<dgrad+scatter>[{dy.rows}x{dy.cols}->{ncols}]", flops=2.0 * dy.rows * dy.cols * ncols, nbytes=4.0 * dy.rows * (2 * dy.cols + ncols))
     _check(_dgrad(DGRAD_SCATTER, ctypes.byref(dy), ncols, _ptr(wp), wp.shape[1], _p(wt), None, 0, None, 0, None, None, None,
                   None, ctypes.byref(gather), _p(dfeat), dfeat.shape[1] if dfeat is not None else 0, _p(dxyz),
                   _p(centre_src), _stream()))
@@ -488,7 +488,7 @@ def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src, wt=None):
 def mlp_wgrad(dy, a, cout, cin, xyz_first, feat_pad, dev):
     ws = _f32(dev, max(1, lib.pn2_mlp_wgrad_workspace(dy.rows, dy.cols, a.cols)))
     dw = _f32(dev, cout, cin)
-    _annotate("gemm_kernel<wgrad>", flops=2.0 * dy.rows * dy.cols * a.cols, nbytes=4.0 * dy.rows * (2 * dy.cols + a.cols))
+    _annotate(f"gemm_kernel<wgrad>[{dy.rows}:{dy.cols}x{a.cols}]", flops=2.0 * dy.rows * dy.cols * a.cols, nbytes=4.0 * dy.rows * (2 * dy.cols + a.cols))
     _check(_wgrad(ctypes.byref(dy), ctypes.byref(a), cout, cin, int(xyz_first), feat_pad, _ptr(ws), _ptr(dw), _stream()))
     _launched(2)
     return dw

@@ -31,10 +31,10 @@
 namespace pn2 {
 namespace {
 
-constexpr int kFpsThreads = 128;  // resident kernel: 4 warps, one per SM sub-partition
+constexpr int kFpsThreads = 512;  // resident kernel: 16 warps = 4 per SM sub-partition (latency hiding for the chain)
 constexpr int kFpsMaxCluster = 16;
 constexpr int kStreamThreads = 512;  // streaming fallback for clouds beyond register capacity
-constexpr int kFpsMaxPts = 48;       // register-resident points per thread (largest instantiation)
+constexpr int kFpsMaxPts = 16;       // register-resident points per thread (largest instantiation)
 
 template <int NW>
 struct alignas(16) FpsSmem {
@@ -116,20 +116,23 @@ __device__ __forceinline__ Cand reduce_candidates(FpsSmem<NW> &S, int p, int j, 
                                                   int warp, int lane) {
   __syncthreads();
   Cand c;
-  c.d = INT_MIN;
-  c.r = 0xffffffffu;
-  c.x = c.y = c.z = 0.f;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) {
-    const uint4 e = S.wkey[p][w];
-    const bool better = (static_cast<int>(e.x) > c.d) || (static_cast<int>(e.x) == c.d && e.y < c.r);
-    if (better) {
-      c.d = static_cast<int>(e.x);
-      c.r = e.y;
-      c.x = __uint_as_float(e.z);
-      c.y = __uint_as_float(e.w);
-      c.z = S.wz[p][w];
+  {  // every warp reduces the NW per-warp candidates with redux (NW <= 32)
+    int ed = INT_MIN;
+    uint32_t er = 0xffffffffu;
+    if (lane < NW) {
+      const uint4 e = S.wkey[p][lane];
+      ed = static_cast<int>(e.x);
+      er = e.y;
     }
+    const int gmax = __reduce_max_sync(0xffffffffu, ed);
+    const uint32_t gr = __reduce_min_sync(0xffffffffu, ed == gmax ? er : 0xffffffffu);
+    const int src = __ffs(__ballot_sync(0xffffffffu, lane < NW && ed == gmax && er == gr)) - 1;
+    const uint4 e = S.wkey[p][src];
+    c.d = static_cast<int>(e.x);
+    c.r = e.y;
+    c.x = __uint_as_float(e.z);
+    c.y = __uint_as_float(e.w);
+    c.z = S.wz[p][src];
   }
   if (cs > 1) {
     if (warp == 0 && lane < cs) {
@@ -174,13 +177,16 @@ __device__ __forceinline__ void setup_cluster(FpsSmem<NW> &S, int cs) {
   }
 }
 
-// ---- register-resident kernel ------------------------------------------------------------------
+// ---- register-resident kernel ------------------------------------------------------------------------------
+// Thread g = cta*512 + tid owns points k = g + i*T, T = cs*512.  T is a multiple of the reference block size
+// bs (a power of two <= 512), so all points of one thread share k mod bs and their tie-break rank grows
+// with i: inside a thread "strict > while scanning i upwards" IS the reference order, and only the warp
+// winner's rank has to be evaluated.
 template <int PTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                     int *__restrict__ idxs, float *__restrict__ new_xyz) {
   constexpr int NW = kFpsThreads / 32;
-  using MaskT = typename std::conditional<(PTS > 32), unsigned long long, uint32_t>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FpsSmem<NW> &S = *reinterpret_cast<FpsSmem<NW> *>(smem_raw);
   float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem<NW>));
@@ -225,26 +231,16 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
   for (int j = 1; j < m; ++j) {
     const int p = j & 1;
     float best = -2.0f;
+    int ib = 0;
 #pragma unroll
     for (int i = 0; i < PTS; ++i) {
       const float d = dist2(px[i], py[i], pz[i], x1, y1, z1);
       const float t = fminf(d, pt[i]);
       pt[i] = t;
-      best = fmaxf(best, t);
+      if (t > best) { best = t; ib = i; }  // strict '>': the lowest i (= lowest rank in this thread) wins ties
     }
     const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(best));
-    MaskT eqm = 0;  // bit i set <=> this thread's point i attains the warp max
-#pragma unroll
-    for (int i = 0; i < PTS; ++i)
-      if (__float_as_int(pt[i]) == wmax) eqm |= MaskT(1) << i;
-    uint32_t myrank = 0xffffffffu;
-    int ib = 0;
-    while (eqm) {  // one iteration on one lane unless the max is tied
-      const int i = (sizeof(MaskT) == 8 ? __ffsll(static_cast<long long>(eqm)) : __ffs(static_cast<int>(eqm))) - 1;
-      eqm &= eqm - 1;
-      const uint32_t r = rank_of(g + i * T, bs_log2);
-      if (r < myrank) { myrank = r; ib = i; }
-    }
+    const uint32_t myrank = (__float_as_int(best) == wmax) ? rank_of(g + ib * T, bs_log2) : 0xffffffffu;
     const uint32_t wrank = __reduce_min_sync(0xffffffffu, myrank);
     if (myrank == wrank) {  // ranks are unique -> exactly one lane
       S.wkey[p][warp] = make_uint4(static_cast<uint32_t>(wmax), wrank, __float_as_uint(sx[ib * kFpsThreads + tid]),
@@ -375,7 +371,7 @@ int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, 
   return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
 }
 
-constexpr int kPtsOptions[] = {1, 2, 4, 8, 16, 20, 26, 32, 40, 48};
+constexpr int kPtsOptions[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
 
 int pick_pts(int need) {
   for (int v : kPtsOptions)
@@ -399,10 +395,10 @@ PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz
   int bs_log2 = 0;
   while ((1 << (bs_log2 + 1)) <= bs) ++bs_log2;
 
-  // Cluster size: smallest that keeps <= 16 points per thread; clouds that need more use 16 CTAs
-  // (8 when the batch would not fit the chip in one wave and registers allow).
+  // Cluster size: smallest that keeps <= 5 points per thread (the per-round critical path is the register
+  // update); halved while the batch would not fit the chip in one wave and registers allow.
   int cs = 1;
-  while (cs < kFpsMaxCluster && (n + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 16) cs *= 2;
+  while (cs < kFpsMaxCluster && (n + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 5) cs *= 2;
   const int sms = sm_count();
   while (cs > 1 && b * cs > sms && (n + (cs / 2) * kFpsThreads - 1) / ((cs / 2) * kFpsThreads) <= kFpsMaxPts) cs /= 2;
   const int need = (n + cs * kFpsThreads - 1) / (cs * kFpsThreads);
@@ -423,14 +419,14 @@ PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz
     return launch_resident<P>(b, n, m, cs, bs_log2, xyz, idxs, new_xyz, stream);
     PN2_FPS_CASE(1)
     PN2_FPS_CASE(2)
+    PN2_FPS_CASE(3)
     PN2_FPS_CASE(4)
+    PN2_FPS_CASE(5)
+    PN2_FPS_CASE(6)
     PN2_FPS_CASE(8)
+    PN2_FPS_CASE(10)
+    PN2_FPS_CASE(12)
     PN2_FPS_CASE(16)
-    PN2_FPS_CASE(20)
-    PN2_FPS_CASE(26)
-    PN2_FPS_CASE(32)
-    PN2_FPS_CASE(40)
-    PN2_FPS_CASE(48)
 #undef PN2_FPS_CASE
   }
   set_error("pn2_furthest_point_sampling: internal dispatch error (pts=%d)", pts);
