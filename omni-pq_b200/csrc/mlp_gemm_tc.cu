@@ -100,26 +100,13 @@ __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int c
   }
 }
 
-// column totals over the 32 lanes of a warp: afterwards lane l holds the sum of v[l] over all lanes
-__device__ __forceinline__ float warp_column_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool upper = (lane & o) != 0;
-#pragma unroll
-    for (int j = 0; j < o; ++j) {
-      const float send = upper ? v[j] : v[j + o];
-      const float keep = upper ? v[j + o] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
-}
-
-// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory.
-// TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and B = activation source are both
-// position rows with channels contiguous, so a k-block is staged transposed (lane = position, 4-byte stores,
-// conflict-free because the 32 lanes of a warp fill one 128-byte swizzle row); blockIdx.z selects a slice of
-// positions and the partial tile goes to out + blockIdx.z * out_split_stride.
+// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory and
+// staged as K-major tiles.  TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and
+// B = activation source are both position rows with channels contiguous, staged as MN-major tiles (the tensor
+// core transposes), blockIdx.z selects a slice of positions and the partial tile goes to
+// out + blockIdx.z * out_split_stride.
+// Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
+// 128-bit access touches 4 lines instead of 32.
 template <int AKIND, int BKIND, bool TRANS, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
@@ -141,12 +128,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
 
-  const uint32_t idesc = idesc_tf32(TM, TN);
+  const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
   const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
@@ -157,104 +140,101 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const int coef_base_a = TRANS ? m0 : 0, coef_base_b = TRANS ? n0 : 0;
   stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
   if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
+  tc_fence_before_sync();
   __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
 
-  // producer mapping, plain form: thread -> one tile row (A: a position, B: an output channel) and 4 of its 8
-  // 16-byte chunks; transposed form: lane -> position inside the k-block, warp -> 16 channels of each operand
-  const int prow = tid & (TM - 1);
-  const int chunk0 = (tid >> 7) * 4;
-  const int tch = warp * 16;
-  const uint32_t toff = static_cast<uint32_t>(((lane >> 2) << 4) | ((lane & 3) << 2));
-  uint32_t off[4];
+  // ---- producer mapping --------------------------------------------------------------------------------
+  // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 32*i (i < 4) of the A / B tile
+  // transposed : q = tid % 32 (4 channels of the tile's 128), positions (tid / 32) + 8*i (i < 4) of the k-block
+  const int chunk = tid & 7, rsub = tid >> 3;
+  const int q = tid & 31, psub = tid >> 5;
+  uint32_t off0;  // smem byte offset of this thread's first 16-byte store inside an operand tile
+  if (!TRANS) off0 = sw128_offset(rsub, chunk);
+  else off0 = static_cast<uint32_t>((q >> 3) * 4096 + psub * 128 + (((q & 7) ^ psub) << 4));  // k = psub (+8i -> +1024 i)
+  constexpr uint32_t kOffStep = TRANS ? 1024u : 4096u;
+
+  RowCtx ca[4], cb[4];
+  auto make_ctx = [&](int kb, RowCtx (&xa)[4], RowCtx (&xb)[4]) {  // transposed form: contexts of a k-block's positions
 #pragma unroll
-  for (int i = 0; i < 4; ++i) off[i] = sw128_offset(prow, chunk0 + i);
-
-  RowCtx ca, cb, ca_next, cb_next;
-  auto make_ctx = [&](int kb, RowCtx &xa, RowCtx &xb) {
-    if (!TRANS) return;
-    const int p = k_begin + kb * TK + lane;
-    const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-    xa = row_ctx<AKIND>(g.A, r);
-    xb = row_ctx<BKIND>(g.B, r);
+    for (int i = 0; i < 4; ++i) {
+      const int p = k_begin + kb * TK + psub + 8 * i;
+      const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
+      xa[i] = row_ctx<AKIND>(g.A, r);
+      xb[i] = row_ctx<BKIND>(g.B, r);
+    }
   };
   if (TRANS) {
     make_ctx(0, ca, cb);
-    make_ctx(1, ca_next, cb_next);
   } else {
-    ca = row_ctx<AKIND>(g.A, m0 + prow);
-    cb = row_ctx<BKIND>(g.B, n0 + prow);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 32 * i);
+      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 32 * i);
+    }
   }
-  auto col_a = [&](int kb, int i) { return TRANS ? m0 + tch + i * 4 : k_begin + kb * TK + (chunk0 + i) * 4; };
-  auto col_b = [&](int kb, int i) { return TRANS ? n0 + tch + i * 4 : k_begin + kb * TK + (chunk0 + i) * 4; };
+  auto col_a = [&](int kb) { return TRANS ? m0 + q * 4 : k_begin + kb * TK + chunk * 4; };
+  auto col_b = [&](int kb) { return TRANS ? n0 + q * 4 : k_begin + kb * TK + chunk * 4; };
 
   Raw ra[4], rb[4], ra_next[4], rb_next[4];
   if (num_kb > 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca, col_a(0, i));
-      rb[i] = fetch_raw<BKIND>(g.B, cb, col_b(0, i));
+      ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
+      rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
     }
   }
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
-    // 1. put the next k-block's loads in flight (transposed form: with the row contexts resolved one block ago)
+    // 1. put the next k-block's loads in flight
+    RowCtx na[4], nb[4];
+    if (TRANS) make_ctx(kb + 1, na, nb);
     if (kb + 1 < num_kb) {
-      const RowCtx &na = TRANS ? ca_next : ca;
-      const RowCtx &nb = TRANS ? cb_next : cb;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        ra_next[i] = fetch_raw<AKIND>(g.A, na, col_a(kb + 1, i));
-        rb_next[i] = fetch_raw<BKIND>(g.B, nb, col_b(kb + 1, i));
+        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
+        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
       }
     }
-    RowCtx ca_nn, cb_nn;
-    make_ctx(kb + 2, ca_nn, cb_nn);
     // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
     if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
     unsigned char *st = tiles + s * STAGE_BYTES;
-    // 3. transform + split + store the current block
+    // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca, col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
-      const float4 vb = apply_raw<BKIND>(g.B, cb, col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
-      if (!TRANS) {
-        float4 hi, lo;
-        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
-      } else {
-        const float a4[4] = {va.x, va.y, va.z, va.w};
-        const float b4[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = tch + i * 4 + e;  // tile row = channel
-          const uint32_t o = static_cast<uint32_t>((c >> 3) * 1024 + (c & 7) * 128) + (toff ^ static_cast<uint32_t>((c & 7) << 4));
-          float hi, lo;
-          split_tf32(a4[e], hi, lo);
-          *reinterpret_cast<float *>(st + 0 * TILE_BYTES + o) = hi;
-          *reinterpret_cast<float *>(st + 1 * TILE_BYTES + o) = lo;
-          split_tf32(b4[e], hi, lo);
-          *reinterpret_cast<float *>(st + 2 * TILE_BYTES + o) = hi;
-          *reinterpret_cast<float *>(st + 3 * TILE_BYTES + o) = lo;
-        }
-      }
+      const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
+      const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
+      const uint32_t o = off0 + i * kOffStep;
+      float4 hi, lo;
+      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+      *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + o) = hi;
+      *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + o) = lo;
+      split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+      split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+      *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + o) = hi;
+      *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + o) = lo;
     }
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
       const uint32_t base = smem_addr(st);
-      const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + TILE_BYTES);
-      const uint64_t b_hi = smem_desc_sw128(base + 2 * TILE_BYTES), b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+      uint64_t a_hi, a_lo, b_hi, b_lo, step;
+      if (!TRANS) {
+        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
+      } else {
+        a_hi = smem_desc_mn_sw128(base, 4096); a_lo = smem_desc_mn_sw128(base + TILE_BYTES, 4096);
+        b_hi = smem_desc_mn_sw128(base + 2 * TILE_BYTES, 4096); b_lo = smem_desc_mn_sw128(base + 3 * TILE_BYTES, 4096);
+        step = 1024 >> 4;  // next group of 8 k-rows
+      }
 #pragma unroll
       for (int ks = 0; ks < TK / 8; ++ks) {
-        const uint64_t adv = static_cast<uint64_t>(ks * 32 >> 4);  // +32 bytes per k-step inside the swizzle row
+        const uint64_t adv = step * ks;
         mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
         mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
         mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
@@ -267,81 +247,100 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     for (int i = 0; i < 4; ++i) {
       ra[i] = ra_next[i];
       rb[i] = rb_next[i];
-    }
-    if (TRANS) {
-      ca = ca_next; cb = cb_next;
-      ca_next = ca_nn; cb_next = cb_nn;
+      if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
     }
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
 
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (rows), warps 0-3 columns 0-63, warps 4-7 columns 64-127
-  const int row = m0 + (warp & 3) * 32 + lane;
-  const int cbase = (warp >> 2) * 64;
-  const bool row_ok = row < g.M;
+  // ---- epilogue -------------------------------------------------------------------------------------------
+  // warp w reads TMEM lanes 32*(w%4)..+31 (tile rows); warps 0-3 take columns 0-63, warps 4-7 columns 64-127.
+  // Each 32x32 chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit
+  // accesses both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
+  float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
+  const int rbase = m0 + (warp & 3) * 32;
+  const int cq = lane & 7, rs = lane >> 3;
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
-    const int c_local = cbase + cc * 32;
-    const int col = n0 + c_local;
-    float v[32];
-    if (num_kb > 0) {
-      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
-    } else {  // empty position slice of a split weight gradient: the accumulator was never written
+    const int c_local = (warp >> 2) * 64 + cc * 32;
+    const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
+    {
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+      } else {  // empty position slice of a split weight gradient: the accumulator was never written
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    }
-    float q[32];  // second statistic operand
-    if (EPI == TC_EPI_DGRAD_MASK) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 y = zero4(), sc = zero4(), sh = zero4();
-        if (row_ok && col + j < g.N) {
-          y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col + j);
-          sc = ldg4(g.prev_scale + col + j);
-          sh = ldg4(g.prev_shift + col + j);
-        }
-        v[j + 0] = fmaf(y.x, sc.x, sh.x) > 0.f ? v[j + 0] : 0.f;
-        v[j + 1] = fmaf(y.y, sc.y, sh.y) > 0.f ? v[j + 1] : 0.f;
-        v[j + 2] = fmaf(y.z, sc.z, sh.z) > 0.f ? v[j + 2] : 0.f;
-        v[j + 3] = fmaf(y.w, sc.w, sh.w) > 0.f ? v[j + 3] : 0.f;
-        q[j + 0] = v[j + 0] * y.x; q[j + 1] = v[j + 1] * y.y; q[j + 2] = v[j + 2] * y.z; q[j + 3] = v[j + 3] * y.w;
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
-    }
-    if (EPI == TC_EPI_SCATTER) {
-      if (row_ok) {  // transpose of the gather: scatter-add into the neighbour's feature row / coordinates
-        const RowCtx gc = row_ctx<PN2_ROWS_GATHER>(g.G, row);
-        const int fc = g.G.feat_cols;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = col + j;
-          if (c < fc) {
-            if (g.dfeat) atomicAdd(g.dfeat + gc.goff * g.ldf + c, v[j]);
-          } else if (c < fc + 3 && g.dxyz && g.G.use_xyz) {
-            const float gv = __fdiv_rn(v[j], g.G.inv_scale);
-            atomicAdd(g.dxyz + gc.goff * 3 + (c - fc), gv);
-            const int centre = row / g.G.nsample, cloud = row / (g.G.npoint * g.G.nsample);
-            atomicAdd(g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3 + (c - fc), -gv);
-          }
-        }
-      }
-    } else if (row_ok) {
-      float *dst = g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        if (col + j < g.N) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
+    __syncwarp();
+    const bool col_ok = col < g.N;
+    float4 sc = zero4(), sh = zero4();
+    if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
+      sc = ldg4(g.prev_scale + col);
+      sh = ldg4(g.prev_shift + col);
+    }
+    float4 s1 = zero4(), s2 = zero4();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = rs + 4 * i;
+      const int row = rbase + rr;
+      float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
+      if (row >= g.M || !col_ok) continue;
+      if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
+        const int cloud = row / (g.G.npoint * g.G.nsample);
+        const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
+        const int fc = g.G.feat_cols;
+        if (col < fc) {
+          if (g.dfeat) {
+            float *dst = g.dfeat + src * g.ldf + col;
+            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+          }
+        } else if (col == fc && g.dxyz && g.G.use_xyz) {
+          const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                      gz = __fdiv_rn(v.z, g.G.inv_scale);
+          float *dn = g.dxyz + src * 3;
+          atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+          const int centre = row / g.G.nsample;
+          float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+          atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+        }
+        continue;
+      }
+      float4 qv;
+      if (EPI == TC_EPI_DGRAD_MASK) {
+        const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+        v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+        v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+        v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+        v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+        qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
+      } else {
+        qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+      }
+      *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+    }
+    __syncwarp();
     if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-      // rows beyond M hold exact zeros (their A rows were zero), so they do not disturb the sums
-      const float s1 = warp_column_sum(v, lane);
-      const float s2 = warp_column_sum(q, lane);
-      red[0][warp][lane] = s1;
-      red[1][warp][lane] = s2;
+      // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+        s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+      }
+      if (lane < 8) {
+        *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
+        *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
+      }
       __syncthreads();
-      if (tid < 64) {  // tid -> (half h = tid/32 selects warps 4h..4h+3, column lane)
+      if (tid < 64) {  // tid -> (half h = tid/32 selects warps 4h..4h+3, column l)
         const int h = tid >> 5, l = tid & 31;
         const int c = n0 + h * 64 + cc * 32 + l;
         if (c < g.stats_ld) {
