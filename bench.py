@@ -262,7 +262,7 @@ def main_ours(args):
             if nbytes:
                 row["gbs"] = nbytes / (ms * 1e-3) / 1e9
             kernels.append(row)
-        gemm_shapes = [{"gemm": n, "us": 1e3 * ms / cnt, "tflops": fl / (ms * 1e-3) / 1e12 if ms else 0.0}
+        gemm_shapes = [{"launch": n, "us": 1e3 * ms / cnt, "tflops": fl / (ms * 1e-3) / 1e12 if ms else 0.0}
                        for n, (ms, cnt, fl) in sorted(shapes.items(), key=lambda kv: -kv[1][0])]
         top = kernels[0]
         if "tflops" in top:
@@ -289,7 +289,7 @@ def main_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": args.batch * args.points * 6 * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "kernels": kernels,
-                "gemm_shapes": gemm_shapes,
+                "shapes": gemm_shapes,
                 "cpu_baseline": cpu_base}
         if not args.no_ref_gpu and world == 1:
             line["ref_gpu"] = ref_gpu_run(args, dev)

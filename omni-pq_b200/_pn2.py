@@ -150,7 +150,7 @@ def furthest_point_sampling(points, nsamples, return_xyz=False):
         tmp = None
         if n > lib.pn2_fps_resident_capacity():
             tmp = torch.empty(b, n, dtype=torch.float32, device=points.device)
-        _annotate("fps_kernel", nbytes=b * (12.0 * n + 16.0 * nsamples))
+        _annotate(f"fps_kernel[{b}x{n}->{nsamples}]", nbytes=b * (12.0 * n + 16.0 * nsamples))
         _check(_fps(b, n, nsamples, _ptr(points), _ptr(tmp) if tmp is not None else None, _ptr(out),
                     _ptr(new_xyz) if return_xyz else None, _stream()))
     _launched()
@@ -193,7 +193,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     n = xyz.shape[1]
     with torch.cuda.device(xyz.device):
         idx = torch.empty(b, m, int(nsample), dtype=torch.int32, device=xyz.device)
-        _annotate("ball_query_kernel", nbytes=b * (12.0 * (n + m) + 4.0 * m * int(nsample)))
+        _annotate(f"ball_query_kernel[{b}x{n}x{m}]", nbytes=b * (12.0 * (n + m) + 4.0 * m * int(nsample)))
         _check(_ball(b, n, m, float(radius), int(nsample), _ptr(new_xyz), _ptr(xyz), _ptr(idx), _stream()))
     _launched()
     return idx
@@ -396,7 +396,7 @@ def bn_finalize(training, tiles, c, np_, count, stats, sums, bn):
                    _p(bn.running_var) if (track or not training) else None,
                    _p(bn.num_batches_tracked) if track else None, mom, float(bn.eps),
                    _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()))
-    _launched(2 if track and bn.num_batches_tracked is not None else 1)
+    _launched(2 if (track and bn.num_batches_tracked is not None and bn.momentum is None) else 1)
     return out[0], out[1], out[2], out[3]
 
 

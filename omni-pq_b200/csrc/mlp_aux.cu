@@ -59,10 +59,10 @@ to_channel_major_kernel(int c, int n, int stride, const float *__restrict__ src,
 }
 
 // ---- BatchNorm statistics ---------------------------------------------------------------------------
-// stats[tiles][2][np] fp32 partials -> fp64 totals.  Block = 32 channels x 8 tile lanes: lane ty walks
-// tiles ty, ty+8, ... (coalesced across the 32 channels), the 8 lane totals are combined in a fixed
+// stats[tiles][2][np] fp32 partials -> fp64 totals.  Block = 32 channels x 32 tile lanes: lane ty walks
+// tiles ty, ty+32, ... (coalesced across the 32 channels), the 32 lane totals are combined in a fixed
 // order through shared memory, so the result is deterministic.  Every thread with ty == 0 gets the totals.
-constexpr int kStatCh = 32, kStatLanes = 8;
+constexpr int kStatCh = 32, kStatLanes = 32;
 
 __device__ __forceinline__ void total_of(const float *stats, int tiles, int np, int ch, bool live, double &s1,
                                          double &s2) {
@@ -106,6 +106,9 @@ __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, doubl
                                    float *__restrict__ shift, float *__restrict__ mean_out,
                                    float *__restrict__ invstd_out) {
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
+  // num_batches_tracked += 1 rides along when the momentum is fixed (nobody reads the counter then); with
+  // momentum=None every channel reads it, so the host launches a separate increment afterwards
+  if (training && nbt && running_mean && momentum >= 0.f && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
   double s1 = 0.0, s2 = 0.0;
   if (training && !sums) total_of(stats, tiles, np, ch, ch < c, s1, s2);  // block-cooperative: before any return
   if (threadIdx.x / kStatCh != 0 || ch >= np) return;
@@ -384,7 +387,7 @@ PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double co
                                                        running_mean, running_var, num_batches_tracked, momentum, eps,
                                                        scale, shift, mean, invstd);
   if (int rc = check_launch("pn2_bn_finalize")) return rc;
-  if (training && num_batches_tracked && running_mean) {
+  if (training && num_batches_tracked && running_mean && momentum < 0.f) {
     bn_bump_counter_kernel<<<1, 1, 0, s>>>(num_batches_tracked);
     return check_launch("pn2_bn_finalize(counter)");
   }

@@ -100,10 +100,12 @@ __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int c
   }
 }
 
-// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory and
-// staged as K-major tiles.  TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and
-// B = activation source are both position rows with channels contiguous, staged as MN-major tiles (the tensor
-// core transposes), blockIdx.z selects a slice of positions and the partial tile goes to
+// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory.
+// TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and B = activation source are both
+// position rows with channels contiguous.  They are transposed while they are staged into the same K-major
+// tiles: a lane holds 4 channels of one position and writes them with four 4-byte stores whose order is
+// rotated per lane, so that the 32 lanes of a store (8 channel quads x 4 consecutive positions) hit 32
+// different banks.  blockIdx.z selects a slice of positions and the partial tile goes to
 // out + blockIdx.z * out_split_stride.
 // Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
 // 128-bit access touches 4 lines instead of 32.
@@ -129,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
 
-  const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
+  const uint32_t idesc = idesc_tf32(TM, TN);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
   const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
@@ -147,26 +149,23 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 
   // ---- producer mapping --------------------------------------------------------------------------------
   // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 32*i (i < 4) of the A / B tile
-  // transposed : q = tid % 32 (4 channels of the tile's 128), positions (tid / 32) + 8*i (i < 4) of the k-block
+  // transposed : cq = lane % 8 (channel quad), pl = lane / 8; position 4*warp + pl of the k-block, channels
+  //              32*i + 4*cq .. +3 (i < 4) of the A / B tile
   const int chunk = tid & 7, rsub = tid >> 3;
-  const int q = tid & 31, psub = tid >> 5;
-  uint32_t off0;  // smem byte offset of this thread's first 16-byte store inside an operand tile
-  if (!TRANS) off0 = sw128_offset(rsub, chunk);
-  else off0 = static_cast<uint32_t>((q >> 3) * 4096 + psub * 128 + (((q & 7) ^ psub) << 4));  // k = psub (+8i -> +1024 i)
-  constexpr uint32_t kOffStep = TRANS ? 1024u : 4096u;
+  const int cq = lane & 7, pl = lane >> 3;
+  const int rot = (cq + (cq >> 2)) & 3;  // per-lane rotation of the 4 stores (bank-conflict-free transpose)
+  uint32_t off0 = 0;
+  if (!TRANS) off0 = sw128_offset(rsub, chunk);  // + 4096 * i
 
   RowCtx ca[4], cb[4];
-  auto make_ctx = [&](int kb, RowCtx (&xa)[4], RowCtx (&xb)[4]) {  // transposed form: contexts of a k-block's positions
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = k_begin + kb * TK + psub + 8 * i;
-      const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-      xa[i] = row_ctx<AKIND>(g.A, r);
-      xb[i] = row_ctx<BKIND>(g.B, r);
-    }
+  auto make_ctx = [&](int kb, RowCtx &xa, RowCtx &xb) {  // transposed form: this lane's position in k-block kb
+    const int p = k_begin + kb * TK + 4 * warp + pl;
+    const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
+    xa = row_ctx<AKIND>(g.A, r);
+    xb = row_ctx<BKIND>(g.B, r);
   };
   if (TRANS) {
-    make_ctx(0, ca, cb);
+    make_ctx(0, ca[0], cb[0]);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -174,64 +173,75 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 32 * i);
     }
   }
-  auto col_a = [&](int kb) { return TRANS ? m0 + q * 4 : k_begin + kb * TK + chunk * 4; };
-  auto col_b = [&](int kb) { return TRANS ? n0 + q * 4 : k_begin + kb * TK + chunk * 4; };
+  auto col_a = [&](int kb, int i) { return TRANS ? m0 + 32 * i + cq * 4 : k_begin + kb * TK + chunk * 4; };
+  auto col_b = [&](int kb, int i) { return TRANS ? n0 + 32 * i + cq * 4 : k_begin + kb * TK + chunk * 4; };
 
   Raw ra[4], rb[4], ra_next[4], rb_next[4];
   if (num_kb > 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
-      rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
+      ra[i] = fetch_raw<AKIND>(g.A, ca[TRANS ? 0 : i], col_a(0, i));
+      rb[i] = fetch_raw<BKIND>(g.B, cb[TRANS ? 0 : i], col_b(0, i));
     }
   }
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
     // 1. put the next k-block's loads in flight
-    RowCtx na[4], nb[4];
+    RowCtx na, nb;
     if (TRANS) make_ctx(kb + 1, na, nb);
     if (kb + 1 < num_kb) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
-        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
+        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na : ca[i], col_a(kb + 1, i));
+        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb : cb[i], col_b(kb + 1, i));
       }
     }
     // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
     if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
     unsigned char *st = tiles + s * STAGE_BYTES;
-    // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
+    // 3. transform + split + store the current block
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
-      const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
-      const uint32_t o = off0 + i * kOffStep;
-      float4 hi, lo;
-      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + o) = hi;
-      *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + o) = lo;
-      split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-      split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + o) = hi;
-      *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + o) = lo;
+      const float4 va = apply_raw<AKIND>(g.A, ca[TRANS ? 0 : i], col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
+      const float4 vb = apply_raw<BKIND>(g.B, cb[TRANS ? 0 : i], col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
+      if (!TRANS) {  // 128-bit stores, 8 lanes fill one swizzled 128-byte row
+        const uint32_t o = off0 + i * 4096u;
+        float4 hi, lo;
+        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + o) = hi;
+        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + o) = lo;
+        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + o) = hi;
+        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + o) = lo;
+      } else {  // transpose: element e of the quad -> tile row (channel) 32i + 4cq + e, k = 4*warp + pl
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = (t + rot) & 3;
+          const float av = e == 0 ? va.x : e == 1 ? va.y : e == 2 ? va.z : va.w;
+          const float bv = e == 0 ? vb.x : e == 1 ? vb.y : e == 2 ? vb.z : vb.w;
+          const int c = 32 * i + 4 * cq + e;
+          const uint32_t o = static_cast<uint32_t>((c >> 3) * 1024 + (c & 7) * 128 + ((warp ^ (c & 7)) << 4) + pl * 4);
+          float hi, lo;
+          split_tf32(av, hi, lo);
+          *reinterpret_cast<float *>(st + 0 * TILE_BYTES + o) = hi;
+          *reinterpret_cast<float *>(st + 1 * TILE_BYTES + o) = lo;
+          split_tf32(bv, hi, lo);
+          *reinterpret_cast<float *>(st + 2 * TILE_BYTES + o) = hi;
+          *reinterpret_cast<float *>(st + 3 * TILE_BYTES + o) = lo;
+        }
+      }
     }
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
       const uint32_t base = smem_addr(st);
-      uint64_t a_hi, a_lo, b_hi, b_lo, step;
-      if (!TRANS) {
-        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
-        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
-      } else {
-        a_hi = smem_desc_mn_sw128(base, 4096); a_lo = smem_desc_mn_sw128(base + TILE_BYTES, 4096);
-        b_hi = smem_desc_mn_sw128(base + 2 * TILE_BYTES, 4096); b_lo = smem_desc_mn_sw128(base + 3 * TILE_BYTES, 4096);
-        step = 1024 >> 4;  // next group of 8 k-rows
-      }
+      const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + TILE_BYTES);
+      const uint64_t b_hi = smem_desc_sw128(base + 2 * TILE_BYTES), b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+      const uint64_t step = 32 >> 4;  // +32 bytes per k-step inside the 128-byte swizzle row
 #pragma unroll
       for (int ks = 0; ks < TK / 8; ++ks) {
         const uint64_t adv = step * ks;
@@ -247,8 +257,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     for (int i = 0; i < 4; ++i) {
       ra[i] = ra_next[i];
       rb[i] = rb_next[i];
-      if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
     }
+    if (TRANS) { ca[0] = na; cb[0] = nb; }
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
@@ -259,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   // accesses both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
   float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
   const int rbase = m0 + (warp & 3) * 32;
-  const int cq = lane & 7, rs = lane >> 3;
+  const int rs = lane >> 3;  // (cq = lane & 7 from above: this lane's column quad)
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     const int c_local = (warp >> 2) * 64 + cc * 32;
