@@ -36,6 +36,8 @@ constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over
 constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
 constexpr uint32_t TMEM_COLS = 128;
 
+constexpr bool kTransMN = true;  // weight gradient: MN-major (32-byte-base swizzle) tiles instead of a transposing store
+
 enum { TC_EPI_STORE = 0, TC_EPI_STORE_STATS = 1, TC_EPI_DGRAD_MASK = 2, TC_EPI_SCATTER = 3 };
 
 
@@ -131,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
 
-  const uint32_t idesc = idesc_tf32(TM, TN);
+  const uint32_t idesc = idesc_tf32(TM, TN, TRANS && kTransMN);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
   const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
@@ -156,16 +158,38 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const int rot = (cq + (cq >> 2)) & 3;  // per-lane rotation of the 4 stores (bank-conflict-free transpose)
   uint32_t off0 = 0;
   if (!TRANS) off0 = sw128_offset(rsub, chunk);  // + 4096 * i
+  // MN-major variant of the transposed form: lane = 16-byte channel quad q of the tile's 128 channels
+  // (a warp reads one position's 512 contiguous bytes), position warp + 8*i of the k-block:
+  //   offset(k, q) = (q/8)*4096 + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
+  const int qq = lane;
+  uint32_t offmn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = warp + 8 * i;
+    offmn[i] = static_cast<uint32_t>((qq >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((qq & 7) >> 1) ^ (k & 3)) << 5) +
+                                     (qq & 1) * 16);
+  }
 
   RowCtx ca[4], cb[4];
-  auto make_ctx = [&](int kb, RowCtx &xa, RowCtx &xb) {  // transposed form: this lane's position in k-block kb
-    const int p = k_begin + kb * TK + 4 * warp + pl;
-    const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-    xa = row_ctx<AKIND>(g.A, r);
-    xb = row_ctx<BKIND>(g.B, r);
+  auto make_ctx = [&](int kb, RowCtx *xa, RowCtx *xb) {  // transposed form: this thread's positions in k-block kb
+    if (kTransMN) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = k_begin + kb * TK + warp + 8 * i;
+        const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
+        xa[i] = row_ctx<AKIND>(g.A, r);
+        xb[i] = row_ctx<BKIND>(g.B, r);
+      }
+    } else {
+      const int p = k_begin + kb * TK + 4 * warp + pl;
+      const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
+      xa[0] = row_ctx<AKIND>(g.A, r);
+      xb[0] = row_ctx<BKIND>(g.B, r);
+    }
   };
+  constexpr bool kCtxPerI = !TRANS || kTransMN;  // one row context per pass i (else one per k-block)
   if (TRANS) {
-    make_ctx(0, ca[0], cb[0]);
+    make_ctx(0, ca, cb);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -173,28 +197,32 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 32 * i);
     }
   }
-  auto col_a = [&](int kb, int i) { return TRANS ? m0 + 32 * i + cq * 4 : k_begin + kb * TK + chunk * 4; };
-  auto col_b = [&](int kb, int i) { return TRANS ? n0 + 32 * i + cq * 4 : k_begin + kb * TK + chunk * 4; };
+  auto col_a = [&](int kb, int i) {
+    return !TRANS ? k_begin + kb * TK + chunk * 4 : kTransMN ? m0 + qq * 4 : m0 + 32 * i + cq * 4;
+  };
+  auto col_b = [&](int kb, int i) {
+    return !TRANS ? k_begin + kb * TK + chunk * 4 : kTransMN ? n0 + qq * 4 : n0 + 32 * i + cq * 4;
+  };
 
   Raw ra[4], rb[4], ra_next[4], rb_next[4];
   if (num_kb > 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca[TRANS ? 0 : i], col_a(0, i));
-      rb[i] = fetch_raw<BKIND>(g.B, cb[TRANS ? 0 : i], col_b(0, i));
+      ra[i] = fetch_raw<AKIND>(g.A, ca[kCtxPerI ? i : 0], col_a(0, i));
+      rb[i] = fetch_raw<BKIND>(g.B, cb[kCtxPerI ? i : 0], col_b(0, i));
     }
   }
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
     // 1. put the next k-block's loads in flight
-    RowCtx na, nb;
+    RowCtx na[4], nb[4];
     if (TRANS) make_ctx(kb + 1, na, nb);
     if (kb + 1 < num_kb) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na : ca[i], col_a(kb + 1, i));
-        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb : cb[i], col_b(kb + 1, i));
+        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[kCtxPerI ? i : 0] : ca[i], col_a(kb + 1, i));
+        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[kCtxPerI ? i : 0] : cb[i], col_b(kb + 1, i));
       }
     }
     // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
@@ -203,10 +231,10 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     // 3. transform + split + store the current block
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca[TRANS ? 0 : i], col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
-      const float4 vb = apply_raw<BKIND>(g.B, cb[TRANS ? 0 : i], col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
-      if (!TRANS) {  // 128-bit stores, 8 lanes fill one swizzled 128-byte row
-        const uint32_t o = off0 + i * 4096u;
+      const float4 va = apply_raw<AKIND>(g.A, ca[kCtxPerI ? i : 0], col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
+      const float4 vb = apply_raw<BKIND>(g.B, cb[kCtxPerI ? i : 0], col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
+      if (!TRANS || kTransMN) {  // 128-bit stores (plain: 8 lanes fill one swizzled 128-byte row)
+        const uint32_t o = TRANS ? offmn[i] : off0 + i * 4096u;
         float4 hi, lo;
         split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
         split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
@@ -239,9 +267,17 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     if (tid == 0) {
       tc_fence_after_sync();
       const uint32_t base = smem_addr(st);
-      const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + TILE_BYTES);
-      const uint64_t b_hi = smem_desc_sw128(base + 2 * TILE_BYTES), b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-      const uint64_t step = 32 >> 4;  // +32 bytes per k-step inside the 128-byte swizzle row
+      uint64_t a_hi, a_lo, b_hi, b_lo, step;
+      if (TRANS && kTransMN) {
+        a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
+        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
+        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
+        step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
+      } else {
+        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
+      }
 #pragma unroll
       for (int ks = 0; ks < TK / 8; ++ks) {
         const uint64_t adv = step * ks;
@@ -258,7 +294,10 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       ra[i] = ra_next[i];
       rb[i] = rb_next[i];
     }
-    if (TRANS) { ca[0] = na; cb[0] = nb; }
+    if (TRANS) {
+#pragma unroll
+      for (int i = 0; i < (kCtxPerI ? 4 : 1); ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+    }
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();

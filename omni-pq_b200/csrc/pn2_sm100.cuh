@@ -104,6 +104,18 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// 32-bit elements in MN-major use the "128B swizzle, 32-byte base" layout (CUTLASS Layout_MN_SW128_32B_Atom:
+// Swizzle<2,5,2> over 128 B x 4 k-rows): the 32-byte chunk index inside a 128-byte row is XORed with
+// (k-row % 4); groups of 4 k-rows are SBO bytes apart, columns of 32 MN elements LBO bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 
 // kind::tf32, fp32 accumulate, M x N tile; mn_major selects MN-major (transposed) A and B operands
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, bool mn_major = false) {
