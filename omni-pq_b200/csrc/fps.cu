@@ -180,46 +180,27 @@ __device__ __forceinline__ void setup_cluster(FpsSmem<NW> &S, int cs) {
 // ---- register-resident kernel ------------------------------------------------------------------------------
 // Thread g = cta*512 + tid owns points k = g + i*T, T = cs*512.  T is a multiple of the reference block size
 // bs (a power of two <= 512), so all points of one thread share k mod bs and their tie-break rank grows
-// with i: inside a thread "strict > while scanning i upwards" IS the reference order.
-//
-// The round is a chain of dependent steps, so the kernel is written to keep that chain short:
-//   registers: 4-5 min-distance updates -> warp arg-max with ONE redux.max; the tie-break rank is only
-//   evaluated by the lane(s) that attain the maximum (a single lane unless distances tie exactly);
-//   CTA: the warp winner does one 64-bit shared-memory atomicMax on the key (distance bits, ~rank), one
-//   bar.sync, every thread reads the winning key back -- no second reduction level;
-//   cluster: the CTA key + the winner's coordinates are pushed to every CTA with st.async (DSMEM,
-//   mbarrier complete_tx) and reduced with one redux.max.
-// Keys are triple-buffered so the reset of a buffer is always two barriers away from its next use.
-struct alignas(16) FpsKeys {
-  long long key[3];                 // CTA arg-max key per round parity (mod 3)
-  long long ckey[2][kFpsMaxCluster];  // keys received from the cluster (mod 2)
-  float4 cxyz[2][kFpsMaxCluster];     // winner coordinates received from the cluster
-  unsigned long long bar[2];
-};
-
-__device__ __forceinline__ long long make_key(int dist_bits, uint32_t rank) {
-  return (static_cast<long long>(dist_bits) << 32) | static_cast<long long>(~rank);
-}
-
+// with i: inside a thread "strict > while scanning i upwards" IS the reference order, and only the warp
+// winner's rank has to be evaluated.
 template <int PTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                     int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  constexpr int NW = kFpsThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FpsKeys &S = *reinterpret_cast<FpsKeys *>(smem_raw);
-  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsKeys));
+  FpsSmem<NW> &S = *reinterpret_cast<FpsSmem<NW> *>(smem_raw);
+  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem<NW>));
   float *sy = sx + PTS * kFpsThreads;
   float *sz = sy + PTS * kFpsThreads;
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
   const int batch = blockIdx.x / cs;
   xyz += static_cast<size_t>(batch) * n * 3;
   idxs += static_cast<size_t>(batch) * m;
   if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
   const int T = cs * kFpsThreads;
-  const int cta_base = static_cast<int>(my_cta) * kFpsThreads;
-  const int g = cta_base + tid;
+  const int g = static_cast<int>(my_cta) * kFpsThreads + tid;
 
   float px[PTS], py[PTS], pz[PTS], pt[PTS];
 #pragma unroll
@@ -245,22 +226,10 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
     idxs[0] = 0;
     if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
   }
-  if (tid < 3) S.key[tid] = LLONG_MIN;
-  if (cs > 1) {
-    if (tid == 0) {
-      mbar_init(&S.bar[0], 1);
-      mbar_init(&S.bar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_arrive_expect_tx(&S.bar[0], cs * 24);
-      mbar_arrive_expect_tx(&S.bar[1], cs * 24);
-    }
-    cluster_sync_all();
-  } else {
-    __syncthreads();
-  }
+  setup_cluster(S, cs);
 
   for (int j = 1; j < m; ++j) {
-    const int p3 = j % 3, p = j & 1;
+    const int p = j & 1;
     float best = -2.0f;
     int ib = 0;
 #pragma unroll
@@ -270,48 +239,20 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
       pt[i] = t;
       if (t > best) { best = t; ib = i; }  // strict '>': the lowest i (= lowest rank in this thread) wins ties
     }
-    const int bits = __float_as_int(best);
-    const int wmax = __reduce_max_sync(0xffffffffu, bits);
-    // normally one lane per warp; exact ties are resolved by the atomic on (dist, ~rank); a warp without any
-    // candidate (all lanes at the -1 sentinel) sends a single key
-    if (bits == wmax && (bits >= 0 || lane == 0))
-      atomicMax(&S.key[p3], make_key(bits, rank_of(g + ib * T, bs_log2)));
-    __syncthreads();
-    long long key = S.key[p3];
-    if (tid == 0) S.key[(j + 2) % 3] = LLONG_MIN;  // reset: next used in round j+2, two barriers from now
-    int d = static_cast<int>(key >> 32);
-    uint32_t r = ~static_cast<uint32_t>(key);
-    {  // winner coordinates from this CTA's shared copy: k = g' + i*T with g' = k mod T inside this CTA
-      const int k = index_of_rank(r, bs_log2);
-      const int slot = d < 0 ? 0 : (k / T) * kFpsThreads + (k % T - cta_base);
-      x1 = sx[slot]; y1 = sy[slot]; z1 = sz[slot];
+    const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+    const uint32_t myrank = (__float_as_int(best) == wmax) ? rank_of(g + ib * T, bs_log2) : 0xffffffffu;
+    const uint32_t wrank = __reduce_min_sync(0xffffffffu, myrank);
+    if (myrank == wrank) {  // ranks are unique -> exactly one lane
+      S.wkey[p][warp] = make_uint4(static_cast<uint32_t>(wmax), wrank, __float_as_uint(sx[ib * kFpsThreads + tid]),
+                                   __float_as_uint(sy[ib * kFpsThreads + tid]));
+      S.wz[p][warp] = sz[ib * kFpsThreads + tid];
     }
-    if (cs > 1) {
-      if (tid < cs) {  // push (key, xyz) of this CTA's winner to CTA `tid`
-        const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), tid);
-        st_async_v4(mapa_u32(smem_u32(&S.cxyz[p][my_cta]), tid), rbar, __float_as_uint(x1), __float_as_uint(y1),
-                    __float_as_uint(z1), 0u);
-        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::
-                         "r"(mapa_u32(smem_u32(&S.ckey[p][my_cta]), tid)), "l"(key), "r"(rbar)
-                     : "memory");
-      }
-      mbar_wait(&S.bar[p], ((j - 1) >> 1) & 1);
-      if (tid == 0) mbar_arrive_expect_tx(&S.bar[p], cs * 24);  // re-arm for round j+2
-      long long ck = LLONG_MIN;
-      if (lane < cs) ck = S.ckey[p][lane];
-      const int cd = static_cast<int>(ck >> 32);
-      const int gmax = __reduce_max_sync(0xffffffffu, cd);
-      const uint32_t cr = (cd == gmax && lane < cs) ? static_cast<uint32_t>(ck) : 0u;  // ~rank: larger = better
-      const uint32_t gr = __reduce_max_sync(0xffffffffu, cr);
-      const int src = __ffs(__ballot_sync(0xffffffffu, lane < cs && cd == gmax && cr == gr)) - 1;
-      const float4 w = S.cxyz[p][src];
-      d = gmax;
-      r = ~gr;
-      x1 = w.x; y1 = w.y; z1 = w.z;
-    }
-    if (d < 0) { x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields index 0
+    const Cand c = reduce_candidates(S, p, j, cs, my_cta, warp, lane);
+    int k = 0;
+    if (c.d < 0) { x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields 0
+    else { k = index_of_rank(c.r, bs_log2); x1 = c.x; y1 = c.y; z1 = c.z; }
     if (g == 0) {
-      idxs[j] = d < 0 ? 0 : index_of_rank(r, bs_log2);
+      idxs[j] = k;
       if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
     }
   }
@@ -420,7 +361,7 @@ template <int PTS>
 int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
                     cudaStream_t stream) {
   auto kernel = fps_resident_kernel<PTS>;
-  const size_t smem = sizeof(FpsKeys) + size_t(3) * PTS * kFpsThreads * sizeof(float);
+  const size_t smem = sizeof(FpsSmem<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
   static thread_local int configured_dev = -1;
   if (!configured_on(configured_dev)) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

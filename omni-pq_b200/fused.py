@@ -17,6 +17,8 @@ keep the reference's (B,C,N) layout, and a module output remembers its position-
 torch is used for memory, streams, autograd bookkeeping and (SyncBatchNorm only) the cross-rank
 all-reduce of the BatchNorm sums; every computation is a libpn2_b200 kernel.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -24,6 +26,19 @@ import torch.nn as nn
 import _pn2 as K
 
 pad4 = K.pad4
+
+# Geometry (FPS -> ball query of every level) depends on coordinates only.  It is enqueued on a side stream
+# so that the FPS chain of level l+1 runs underneath the shared MLP of level l instead of in front of it;
+# the MLP stream waits on one event per level.  PN2_GEOM_STREAM=0 keeps everything on the current stream.
+_SIDE_STREAM = os.environ.get("PN2_GEOM_STREAM", "1") != "0"
+_geom_streams = {}
+
+
+def _geom_stream(device):
+    s = _geom_streams.get(device.index)
+    if s is None:
+        s = _geom_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
 
 
 # ---- what the fused path accepts ------------------------------------------------------------------------
@@ -200,16 +215,34 @@ def _flat_params(layers):
 # ---- set abstraction -------------------------------------------------------------------------------------
 class _SAFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, layers, feat_cached, xyz, features, inds, *params):
+    def forward(ctx, module, layers, feat_cached, xyz_on_side, xyz, features, inds, *params):
         b, n, _ = xyz.shape
         m, ns = module.npoint, module.nsample
-        xyz_c = xyz.detach().contiguous()
-        if inds is None:
-            inds, new_xyz = K.furthest_point_sampling(xyz_c, m, return_xyz=True)
+
+        def geometry():
+            xyz_c = xyz.detach().contiguous()
+            if inds is None:
+                inds_, new_xyz = K.furthest_point_sampling(xyz_c, m, return_xyz=True)
+            else:
+                inds_ = inds.contiguous()
+                new_xyz = K.gather_points(xyz_c.transpose(1, 2).contiguous(), inds_).transpose(1, 2).contiguous()
+            return xyz_c, inds_, new_xyz, K.ball_query(new_xyz, xyz_c, module.radius, ns)
+
+        if _SIDE_STREAM and not torch.cuda.is_current_stream_capturing():
+            main, side = torch.cuda.current_stream(xyz.device), _geom_stream(xyz.device)
+            if not xyz_on_side or inds is not None:
+                side.wait_stream(main)  # coordinates (or given indices) were produced on the MLP stream
+            with torch.cuda.stream(side):
+                xyz_c, inds, new_xyz, idx = geometry()
+                ready = torch.cuda.Event()
+                ready.record(side)
+            xyz.record_stream(side)
+            xyz_c.record_stream(side)
+            main.wait_event(ready)
+            for t in (inds, new_xyz, idx):
+                t.record_stream(main)
         else:
-            inds = inds.contiguous()
-            new_xyz = K.gather_points(xyz_c.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
-        idx = K.ball_query(new_xyz, xyz_c, module.radius, ns)
+            xyz_c, inds, new_xyz, idx = geometry()
         if features is not None:
             c_feat = features.shape[1]
             feat_pm = _point_major(features, feat_cached)
@@ -238,7 +271,7 @@ class _SAFunction(torch.autograd.Function):
     def backward(ctx, g_new_xyz, g_out, _g_inds, _g_pm):
         state, rows0, nrows, arg, (b, n, m, ns, c_feat, ldf) = ctx.pn2
         _new_xyz, inds, out_pm = ctx.saved_tensors
-        need_xyz, need_feat = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_xyz, need_feat = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
         dev = out_pm.device
         dxyz = dfeat = None
         grads = [None] * (3 * len(state))
@@ -264,14 +297,17 @@ class _SAFunction(torch.autograd.Function):
             dxyz = g if dxyz is None else dxyz + g
         if need_xyz and dxyz is None:
             dxyz = torch.zeros(b, n, 3, dtype=torch.float32, device=dev)
-        return (None, None, None, dxyz, dfeat, None, *grads)
+        return (None, None, None, None, dxyz, dfeat, None, *grads)
 
 
 def sa_forward(module, xyz, features, inds):
     layers = _mlp_layers(module.mlp_module)
-    new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), xyz, features, inds,
+    on_side = getattr(xyz, "_pn2_side", None) == (xyz._version, tuple(xyz.shape))
+    new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), on_side, xyz, features, inds,
                                                    *_flat_params(layers))
     _remember_pm(out, out_pm)
+    if _SIDE_STREAM:
+        new_xyz._pn2_side = (new_xyz._version, tuple(new_xyz.shape))  # produced on the geometry stream
     return new_xyz, out, inds
 
 
