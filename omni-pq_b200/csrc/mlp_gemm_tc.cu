@@ -27,7 +27,8 @@ namespace {
 using namespace sm100;
 
 constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;                    // 16 warps: latency hiding for the producers / epilogue
+constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
@@ -35,8 +36,6 @@ constexpr int TC_KMAX = 1152;                        // largest K of the non-tra
 constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over K (or over 128 tile channels); B: 2 x 128
 constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
 constexpr uint32_t TMEM_COLS = 128;
-
-constexpr bool kTransMN = true;  // weight gradient: MN-major (32-byte-base swizzle) tiles instead of a transposing store
 
 enum { TC_EPI_STORE = 0, TC_EPI_STORE_STATS = 1, TC_EPI_DGRAD_MASK = 2, TC_EPI_SCATTER = 3 };
 
@@ -121,7 +120,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
   float *coef_a = reinterpret_cast<float *>(tiles + TC_STAGES * STAGE_BYTES + 256);  // [3][coef_ld_a]
   float *coef_b = coef_a + 3 * TC_KMAX;                                              // [2][128]
-  __shared__ float red[2][8][32];  // per-warp column partials for the statistics epilogues
+  __shared__ float red[2][TC_THREADS / 32][32];  // per-warp column partials for the statistics epilogues
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
@@ -133,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
 
-  const uint32_t idesc = idesc_tf32(TM, TN, TRANS && kTransMN);
+  const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
   const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
@@ -150,117 +149,84 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
 
   // ---- producer mapping --------------------------------------------------------------------------------
-  // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 32*i (i < 4) of the A / B tile
-  // transposed : cq = lane % 8 (channel quad), pl = lane / 8; position 4*warp + pl of the k-block, channels
-  //              32*i + 4*cq .. +3 (i < 4) of the A / B tile
+  // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 64*i (i < 2) of the A / B tile
+  // transposed : lane = 16-byte channel quad of the tile's 128 channels (a warp reads one position's 512
+  //              contiguous bytes), positions warp + 16*i (i < 2) of the k-block, stored MN-major:
+  //              offset(k, q) = (q/8)*4096 + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
+  constexpr int R = TC_ROWS_PER_THREAD;
   const int chunk = tid & 7, rsub = tid >> 3;
-  const int cq = lane & 7, pl = lane >> 3;
-  const int rot = (cq + (cq >> 2)) & 3;  // per-lane rotation of the 4 stores (bank-conflict-free transpose)
-  uint32_t off0 = 0;
-  if (!TRANS) off0 = sw128_offset(rsub, chunk);  // + 4096 * i
-  // MN-major variant of the transposed form: lane = 16-byte channel quad q of the tile's 128 channels
-  // (a warp reads one position's 512 contiguous bytes), position warp + 8*i of the k-block:
-  //   offset(k, q) = (q/8)*4096 + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
-  const int qq = lane;
-  uint32_t offmn[4];
+  uint32_t off[R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = warp + 8 * i;
-    offmn[i] = static_cast<uint32_t>((qq >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((qq & 7) >> 1) ^ (k & 3)) << 5) +
-                                     (qq & 1) * 16);
+  for (int i = 0; i < R; ++i) {
+    if (!TRANS) {
+      off[i] = sw128_offset(rsub + 64 * i, chunk);
+    } else {
+      const int k = warp + 16 * i;
+      off[i] = static_cast<uint32_t>((lane >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((lane & 7) >> 1) ^ (k & 3)) << 5) +
+                                     (lane & 1) * 16);
+    }
   }
 
-  RowCtx ca[4], cb[4];
+  RowCtx ca[R], cb[R];
   auto make_ctx = [&](int kb, RowCtx *xa, RowCtx *xb) {  // transposed form: this thread's positions in k-block kb
-    if (kTransMN) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = k_begin + kb * TK + warp + 8 * i;
-        const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-        xa[i] = row_ctx<AKIND>(g.A, r);
-        xb[i] = row_ctx<BKIND>(g.B, r);
-      }
-    } else {
-      const int p = k_begin + kb * TK + 4 * warp + pl;
+    for (int i = 0; i < R; ++i) {
+      const int p = k_begin + kb * TK + warp + 16 * i;
       const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-      xa[0] = row_ctx<AKIND>(g.A, r);
-      xb[0] = row_ctx<BKIND>(g.B, r);
+      xa[i] = row_ctx<AKIND>(g.A, r);
+      xb[i] = row_ctx<BKIND>(g.B, r);
     }
   };
-  constexpr bool kCtxPerI = !TRANS || kTransMN;  // one row context per pass i (else one per k-block)
   if (TRANS) {
     make_ctx(0, ca, cb);
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 32 * i);
-      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 32 * i);
+    for (int i = 0; i < R; ++i) {
+      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 64 * i);
     }
   }
-  auto col_a = [&](int kb, int i) {
-    return !TRANS ? k_begin + kb * TK + chunk * 4 : kTransMN ? m0 + qq * 4 : m0 + 32 * i + cq * 4;
-  };
-  auto col_b = [&](int kb, int i) {
-    return !TRANS ? k_begin + kb * TK + chunk * 4 : kTransMN ? n0 + qq * 4 : n0 + 32 * i + cq * 4;
-  };
+  auto col_a = [&](int kb) { return TRANS ? m0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
+  auto col_b = [&](int kb) { return TRANS ? n0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
 
-  Raw ra[4], rb[4], ra_next[4], rb_next[4];
+  Raw ra[R], rb[R], ra_next[R], rb_next[R];
   if (num_kb > 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca[kCtxPerI ? i : 0], col_a(0, i));
-      rb[i] = fetch_raw<BKIND>(g.B, cb[kCtxPerI ? i : 0], col_b(0, i));
+    for (int i = 0; i < R; ++i) {
+      ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
+      rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
     }
   }
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
     // 1. put the next k-block's loads in flight
-    RowCtx na[4], nb[4];
+    RowCtx na[R], nb[R];
     if (TRANS) make_ctx(kb + 1, na, nb);
     if (kb + 1 < num_kb) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[kCtxPerI ? i : 0] : ca[i], col_a(kb + 1, i));
-        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[kCtxPerI ? i : 0] : cb[i], col_b(kb + 1, i));
+      for (int i = 0; i < R; ++i) {
+        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
+        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
       }
     }
     // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
     if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
     unsigned char *st = tiles + s * STAGE_BYTES;
-    // 3. transform + split + store the current block
+    // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca[kCtxPerI ? i : 0], col_a(kb, i), ra[i], coef_a, coef_ld_a, coef_base_a);
-      const float4 vb = apply_raw<BKIND>(g.B, cb[kCtxPerI ? i : 0], col_b(kb, i), rb[i], coef_b, 128, coef_base_b);
-      if (!TRANS || kTransMN) {  // 128-bit stores (plain: 8 lanes fill one swizzled 128-byte row)
-        const uint32_t o = TRANS ? offmn[i] : off0 + i * 4096u;
-        float4 hi, lo;
-        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + o) = hi;
-        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + o) = lo;
-        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + o) = hi;
-        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + o) = lo;
-      } else {  // transpose: element e of the quad -> tile row (channel) 32i + 4cq + e, k = 4*warp + pl
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int e = (t + rot) & 3;
-          const float av = e == 0 ? va.x : e == 1 ? va.y : e == 2 ? va.z : va.w;
-          const float bv = e == 0 ? vb.x : e == 1 ? vb.y : e == 2 ? vb.z : vb.w;
-          const int c = 32 * i + 4 * cq + e;
-          const uint32_t o = static_cast<uint32_t>((c >> 3) * 1024 + (c & 7) * 128 + ((warp ^ (c & 7)) << 4) + pl * 4);
-          float hi, lo;
-          split_tf32(av, hi, lo);
-          *reinterpret_cast<float *>(st + 0 * TILE_BYTES + o) = hi;
-          *reinterpret_cast<float *>(st + 1 * TILE_BYTES + o) = lo;
-          split_tf32(bv, hi, lo);
-          *reinterpret_cast<float *>(st + 2 * TILE_BYTES + o) = hi;
-          *reinterpret_cast<float *>(st + 3 * TILE_BYTES + o) = lo;
-        }
-      }
+    for (int i = 0; i < R; ++i) {
+      const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
+      const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
+      float4 hi, lo;
+      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+      *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
+      *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
+      split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+      split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+      *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
+      *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -268,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       tc_fence_after_sync();
       const uint32_t base = smem_addr(st);
       uint64_t a_hi, a_lo, b_hi, b_lo, step;
-      if (TRANS && kTransMN) {
+      if (TRANS) {
         a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
         b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
         b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
@@ -290,117 +256,109 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     }
     // 4. rotate the prefetch registers
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
       ra[i] = ra_next[i];
       rb[i] = rb_next[i];
-    }
-    if (TRANS) {
-#pragma unroll
-      for (int i = 0; i < (kCtxPerI ? 4 : 1); ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+      if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
     }
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
 
   // ---- epilogue -------------------------------------------------------------------------------------------
-  // warp w reads TMEM lanes 32*(w%4)..+31 (tile rows); warps 0-3 take columns 0-63, warps 4-7 columns 64-127.
-  // Each 32x32 chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit
-  // accesses both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
+  // 16 warps, one 32 x 32 chunk each: warp w reads TMEM lanes 32*(w%4)..+31 (tile rows), columns 32*(w/4)..+31.
+  // The chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit accesses
+  // both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
   float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
   const int rbase = m0 + (warp & 3) * 32;
-  const int rs = lane >> 3;  // (cq = lane & 7 from above: this lane's column quad)
+  const int cq = lane & 7, rs = lane >> 3;
+  const int c_local = (warp >> 2) * 32;
+  const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
+  {
+    float v[32];
+    if (num_kb > 0) {
+      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+    } else {  // empty position slice of a split weight gradient: the accumulator was never written
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c_local = (warp >> 2) * 64 + cc * 32;
-    const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
-    {
-      float v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
-      } else {  // empty position slice of a split weight gradient: the accumulator was never written
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    __syncwarp();
-    const bool col_ok = col < g.N;
-    float4 sc = zero4(), sh = zero4();
-    if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
-      sc = ldg4(g.prev_scale + col);
-      sh = ldg4(g.prev_shift + col);
-    }
-    float4 s1 = zero4(), s2 = zero4();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = rs + 4 * i;
-      const int row = rbase + rr;
-      float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
-      if (row >= g.M || !col_ok) continue;
-      if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
-        const int cloud = row / (g.G.npoint * g.G.nsample);
-        const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
-        const int fc = g.G.feat_cols;
-        if (col < fc) {
-          if (g.dfeat) {
-            float *dst = g.dfeat + src * g.ldf + col;
-            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-          }
-        } else if (col == fc && g.dxyz && g.G.use_xyz) {
-          const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
-                      gz = __fdiv_rn(v.z, g.G.inv_scale);
-          float *dn = g.dxyz + src * 3;
-          atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
-          const int centre = row / g.G.nsample;
-          float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
-          atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  __syncwarp();
+  const bool col_ok = col < g.N;
+  float4 sc = zero4(), sh = zero4();
+  if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
+    sc = ldg4(g.prev_scale + col);
+    sh = ldg4(g.prev_shift + col);
+  }
+  float4 s1 = zero4(), s2 = zero4();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = rs + 4 * i;
+    const int row = rbase + rr;
+    float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
+    if (row >= g.M || !col_ok) continue;
+    if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
+      const int cloud = row / (g.G.npoint * g.G.nsample);
+      const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
+      const int fc = g.G.feat_cols;
+      if (col < fc) {
+        if (g.dfeat) {
+          float *dst = g.dfeat + src * g.ldf + col;
+          atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
         }
-        continue;
+      } else if (col == fc && g.dxyz && g.G.use_xyz) {
+        const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                    gz = __fdiv_rn(v.z, g.G.inv_scale);
+        float *dn = g.dxyz + src * 3;
+        atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+        const int centre = row / g.G.nsample;
+        float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+        atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
       }
-      float4 qv;
-      if (EPI == TC_EPI_DGRAD_MASK) {
-        const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
-        v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
-        v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
-        v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
-        v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
-        qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
-      } else {
-        qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-      }
-      *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
-      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-      s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+      continue;
     }
-    __syncwarp();
-    if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-      // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
+    float4 qv;
+    if (EPI == TC_EPI_DGRAD_MASK) {
+      const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+      v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+      v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+      v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+      v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+      qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
+    } else {
+      qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+    *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+  }
+  if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
+    // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-        s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+    for (int o = 8; o <= 16; o <<= 1) {
+      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+    }
+    if (lane < 8) {
+      *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
+      *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
+    }
+    __syncthreads();
+    if (tid < 128) {  // tid -> (column group h = tid/32: warps 4h..4h+3 hold its four row blocks, column l)
+      const int h = tid >> 5, l = tid & 31;
+      const int c = n0 + h * 32 + l;
+      if (c < g.stats_ld) {
+        const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
+        const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
+        float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + c;
+        dst[0] = a;
+        dst[g.stats_ld] = b;
       }
-      if (lane < 8) {
-        *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
-        *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
-      }
-      __syncthreads();
-      if (tid < 64) {  // tid -> (half h = tid/32 selects warps 4h..4h+3, column l)
-        const int h = tid >> 5, l = tid & 31;
-        const int c = n0 + h * 64 + cc * 32 + l;
-        if (c < g.stats_ld) {
-          const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
-          const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
-          float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + c;
-          dst[0] = a;
-          dst[g.stats_ld] = b;
-        }
-      }
-      __syncthreads();
     }
   }
 

@@ -31,6 +31,7 @@ pad4 = K.pad4
 # so that the FPS chain of level l+1 runs underneath the shared MLP of level l instead of in front of it;
 # the MLP stream waits on one event per level.  PN2_GEOM_STREAM=0 keeps everything on the current stream.
 _SIDE_STREAM = os.environ.get("PN2_GEOM_STREAM", "1") != "0"
+_SIDE_IN_GRAPH = os.environ.get("PN2_GEOM_STREAM_IN_GRAPH", "1") != "0"  # fork/join the side stream inside CUDA-graph capture
 _geom_streams = {}
 
 
@@ -228,7 +229,7 @@ class _SAFunction(torch.autograd.Function):
                 new_xyz = K.gather_points(xyz_c.transpose(1, 2).contiguous(), inds_).transpose(1, 2).contiguous()
             return xyz_c, inds_, new_xyz, K.ball_query(new_xyz, xyz_c, module.radius, ns)
 
-        if _SIDE_STREAM and not torch.cuda.is_current_stream_capturing():
+        if _SIDE_STREAM and (_SIDE_IN_GRAPH or not torch.cuda.is_current_stream_capturing()):
             main, side = torch.cuda.current_stream(xyz.device), _geom_stream(xyz.device)
             if not xyz_on_side or inds is not None:
                 side.wait_stream(main)  # coordinates (or given indices) were produced on the MLP stream
