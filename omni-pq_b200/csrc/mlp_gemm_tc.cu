@@ -90,9 +90,10 @@ __device__ __forceinline__ float4 apply_raw(const pn2_rows &s, const RowCtx &c, 
 }
 
 template <int KIND>
-__device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int coef_ld, int base, int count, int tid) {
+__device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int coef_ld, int base, int count, int tid,
+                                           int nthreads = TC_THREADS) {
   if (KIND == PN2_ROWS_PLAIN || KIND == PN2_ROWS_GATHER) return;
-  for (int i = tid; i < count; i += TC_THREADS) {
+  for (int i = tid; i < count; i += nthreads) {
     const int c = base + i;
     const bool ok = c < s.cols;
     coef[i] = ok ? __ldg(s.c0 + c) : 0.f;
@@ -378,7 +379,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 constexpr int PT_PRODUCERS = 256, PT_EPILOGUE = 128, PT_THREADS = PT_PRODUCERS + PT_EPILOGUE;
 constexpr int PT_STAGES = 3;
 constexpr int PT_SCRATCH = 4 * 32 * 36 * 4;  // one 32x36 fp32 transpose tile per epilogue warp
-constexpr int PT_SMEM = PT_STAGES * STAGE_BYTES + 1024 + 256 + 3 * TC_KMAX * 4 + PT_SCRATCH;
+constexpr int PT_KMAX = 768;  // largest K whose per-channel coefficients fit next to 3 stages (else: one-tile kernel)
+constexpr int PT_SMEM = PT_STAGES * STAGE_BYTES + 1024 + 256 + 3 * PT_KMAX * 4 + PT_SCRATCH;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -396,8 +398,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
   uint64_t *acc_full = empty_bar + PT_STAGES;                                           // [2]
   uint64_t *acc_empty = acc_full + 2;                                                   // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *coef_a = reinterpret_cast<float *>(tiles + PT_STAGES * STAGE_BYTES + 256);     // [3][TC_KMAX]
-  float *scratch = coef_a + 3 * TC_KMAX;
+  float *coef_a = reinterpret_cast<float *>(tiles + PT_STAGES * STAGE_BYTES + 256);     // [3][PT_KMAX]
+  float *scratch = coef_a + 3 * PT_KMAX;
   __shared__ float red[2][4][128];  // per-epilogue-warp column partials of one tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -411,7 +413,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
-  stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid % PT_PRODUCERS);  // (both halves write: harmless)
+  stage_coef<AKIND>(g.A, coef_a, PT_KMAX, 0, min(g.K, PT_KMAX), tid, PT_THREADS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -464,8 +466,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
         const int kc = kb * TK + chunk * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 va = apply_raw<AKIND>(g.A, ca[i], kc, ra[i], coef_a, TC_KMAX, 0);
-          const float4 vb = apply_raw<PN2_ROWS_PLAIN>(g.B, cb[i], kc, rb[i], coef_a, TC_KMAX, 0);
+          const float4 va = apply_raw<AKIND>(g.A, ca[i], kc, ra[i], coef_a, PT_KMAX, 0);
+          const float4 vb = apply_raw<PN2_ROWS_PLAIN>(g.B, cb[i], kc, rb[i], coef_a, PT_KMAX, 0);
           float4 hi, lo;
           split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
           split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
@@ -668,9 +670,11 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     const char *e = getenv("PN2_TC_PERSISTENT");
     return e == nullptr || e[0] != '0';
   }();
+  const bool needs_coef = akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER;
+  const bool use_pt = persistent && !(needs_coef && g.K > PT_KMAX);
 #define PN2_TC_CASE(AK, EP)                                                   \
   if (akind == AK && epi == EP)                                               \
-    return persistent ? launch_tc_persistent<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
+    return use_pt ? launch_tc_persistent<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)
