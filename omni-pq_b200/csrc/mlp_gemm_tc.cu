@@ -138,16 +138,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
   const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
 
-  // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
-  // tile's 128 output rows / columns for the transposed form)
   const int coef_ld_a = TRANS ? 128 : TC_KMAX;
   const int coef_base_a = TRANS ? m0 : 0, coef_base_b = TRANS ? n0 : 0;
-  stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
-  if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
 
   // ---- producer mapping --------------------------------------------------------------------------------
   // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 64*i (i < 2) of the A / B tile
@@ -198,6 +190,15 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
     }
   }
+
+  // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
+  // tile's 128 output rows / columns for the transposed form); staged while the first k-block's loads fly
+  stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
+  if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
@@ -666,9 +667,12 @@ bool gemm_tc_enabled() {
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
+  // The persistent, warp-specialised variant is correct but measured slower than one tile per 512-thread CTA
+  // (profiles/r1_gemm_bench_*): with only 8 producer warps the operand staging, not the prologue/epilogue,
+  // becomes the bottleneck.  It stays selectable for experiments: PN2_TC_PERSISTENT=1.
   static const bool persistent = [] {
     const char *e = getenv("PN2_TC_PERSISTENT");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';
   }();
   const bool needs_coef = akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER;
   const bool use_pt = persistent && !(needs_coef && g.K > PT_KMAX);
