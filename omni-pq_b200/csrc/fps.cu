@@ -180,16 +180,45 @@ __device__ __forceinline__ void setup_cluster(FpsSmem<NW> &S, int cs) {
 // ---- register-resident kernel ------------------------------------------------------------------------------
 // Thread g = cta*512 + tid owns points k = g + i*T, T = cs*512.  T is a multiple of the reference block size
 // bs (a power of two <= 512), so all points of one thread share k mod bs and their tie-break rank grows
-// with i: inside a thread "strict > while scanning i upwards" IS the reference order, and only the warp
-// winner's rank has to be evaluated.
+// with i: inside a thread "strict > while scanning i upwards" IS the reference order.
+//
+// A round is a chain of dependent steps, so candidates carry the point index k itself and the tie-break rank
+// (bit-reversed slot, stripe) is only evaluated when two candidates of a level have EXACTLY the same distance
+// -- a warp-uniform, rarely taken branch.  The common path per level is one redux.max, one ballot and one
+// popc; no rank arithmetic and no index decoding sit on the critical path.
+struct FpsCand {
+  int d;  // float bits of the min-distance (>= 0), or of the -1 "no candidate" sentinel (< 0)
+  int k;  // point index
+  float x, y, z;
+};
+
+// arg-max over the lanes' (d, k): returns the winning lane (ties -> smallest reference rank)
+__device__ __forceinline__ int warp_argmax_lane(int d, int k, bool active, int bs_log2) {
+  const int dm = __reduce_max_sync(0xffffffffu, active ? d : INT_MIN);
+  const unsigned eq = __ballot_sync(0xffffffffu, active && d == dm);
+  if (__popc(eq) == 1) return __ffs(eq) - 1;
+  const uint32_t r = (active && d == dm) ? rank_of(k, bs_log2) : 0xffffffffu;  // exact tie: reference order
+  const uint32_t rm = __reduce_min_sync(0xffffffffu, r);
+  return __ffs(__ballot_sync(0xffffffffu, r == rm)) - 1;
+}
+
+template <int NW>
+struct alignas(16) FpsSmem2 {
+  uint4 wcand[2][NW];             // per-warp candidate {d, k, x bits, y bits}
+  uint4 ccand[2][kFpsMaxCluster]; // per-CTA candidates received from the cluster
+  float wz[2][NW];
+  float cz[2][kFpsMaxCluster];
+  unsigned long long bar[2];
+};
+
 template <int PTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                     int *__restrict__ idxs, float *__restrict__ new_xyz) {
   constexpr int NW = kFpsThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FpsSmem<NW> &S = *reinterpret_cast<FpsSmem<NW> *>(smem_raw);
-  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem<NW>));
+  FpsSmem2<NW> &S = *reinterpret_cast<FpsSmem2<NW> *>(smem_raw);
+  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem2<NW>));
   float *sy = sx + PTS * kFpsThreads;
   float *sz = sy + PTS * kFpsThreads;
 
@@ -226,7 +255,16 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
     idxs[0] = 0;
     if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
   }
-  setup_cluster(S, cs);
+  if (cs > 1) {
+    if (tid == 0) {
+      mbar_init(&S.bar[0], 1);
+      mbar_init(&S.bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_arrive_expect_tx(&S.bar[0], cs * kCandBytes);
+      mbar_arrive_expect_tx(&S.bar[1], cs * kCandBytes);
+    }
+    cluster_sync_all();
+  }
 
   for (int j = 1; j < m; ++j) {
     const int p = j & 1;
@@ -239,20 +277,47 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
       pt[i] = t;
       if (t > best) { best = t; ib = i; }  // strict '>': the lowest i (= lowest rank in this thread) wins ties
     }
-    const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(best));
-    const uint32_t myrank = (__float_as_int(best) == wmax) ? rank_of(g + ib * T, bs_log2) : 0xffffffffu;
-    const uint32_t wrank = __reduce_min_sync(0xffffffffu, myrank);
-    if (myrank == wrank) {  // ranks are unique -> exactly one lane
-      S.wkey[p][warp] = make_uint4(static_cast<uint32_t>(wmax), wrank, __float_as_uint(sx[ib * kFpsThreads + tid]),
-                                   __float_as_uint(sy[ib * kFpsThreads + tid]));
-      S.wz[p][warp] = sz[ib * kFpsThreads + tid];
+    // ---- warp level ----
+    const int bits = __float_as_int(best);
+    const int kmine = g + ib * T;
+    if (lane == warp_argmax_lane(bits, kmine, true, bs_log2)) {
+      const int slot = ib * kFpsThreads + tid;
+      S.wcand[p][warp] = make_uint4(static_cast<uint32_t>(bits), static_cast<uint32_t>(kmine), __float_as_uint(sx[slot]),
+                                    __float_as_uint(sy[slot]));
+      S.wz[p][warp] = sz[slot];
     }
-    const Cand c = reduce_candidates(S, p, j, cs, my_cta, warp, lane);
-    int k = 0;
-    if (c.d < 0) { x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields 0
-    else { k = index_of_rank(c.r, bs_log2); x1 = c.x; y1 = c.y; z1 = c.z; }
+    __syncthreads();
+    // ---- CTA level (every warp redundantly) ----
+    FpsCand c;
+    {
+      uint4 e = make_uint4(0u, 0u, 0u, 0u);
+      if (lane < NW) e = S.wcand[p][lane];
+      const int src = warp_argmax_lane(static_cast<int>(e.x), static_cast<int>(e.y), lane < NW, bs_log2);
+      const uint4 w = S.wcand[p][src];
+      c.d = static_cast<int>(w.x); c.k = static_cast<int>(w.y);
+      c.x = __uint_as_float(w.z); c.y = __uint_as_float(w.w); c.z = S.wz[p][src];
+    }
+    // ---- cluster level ----
+    if (cs > 1) {
+      if (warp == 0 && lane < cs) {
+        const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+        st_async_v4(mapa_u32(smem_u32(&S.ccand[p][my_cta]), lane), rbar, static_cast<uint32_t>(c.d),
+                    static_cast<uint32_t>(c.k), __float_as_uint(c.x), __float_as_uint(c.y));
+        st_async_b32(mapa_u32(smem_u32(&S.cz[p][my_cta]), lane), rbar, __float_as_uint(c.z));
+      }
+      mbar_wait(&S.bar[p], ((j - 1) >> 1) & 1);
+      if (tid == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCandBytes);  // re-arm for round j+2
+      uint4 e = make_uint4(0u, 0u, 0u, 0u);
+      if (lane < cs) e = S.ccand[p][lane];
+      const int src = warp_argmax_lane(static_cast<int>(e.x), static_cast<int>(e.y), lane < cs, bs_log2);
+      const uint4 w = S.ccand[p][src];
+      c.d = static_cast<int>(w.x); c.k = static_cast<int>(w.y);
+      c.x = __uint_as_float(w.z); c.y = __uint_as_float(w.w); c.z = S.cz[p][src];
+    }
+    if (c.d < 0) { c.k = 0; x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields index 0
+    else { x1 = c.x; y1 = c.y; z1 = c.z; }
     if (g == 0) {
-      idxs[j] = k;
+      idxs[j] = c.k;
       if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
     }
   }
@@ -361,7 +426,7 @@ template <int PTS>
 int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
                     cudaStream_t stream) {
   auto kernel = fps_resident_kernel<PTS>;
-  const size_t smem = sizeof(FpsSmem<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
+  const size_t smem = sizeof(FpsSmem2<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
   static thread_local int configured_dev = -1;
   if (!configured_on(configured_dev)) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
