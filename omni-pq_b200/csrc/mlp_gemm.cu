@@ -417,9 +417,13 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
   PN2_REQUIRE((dfeat == nullptr || ldf >= gather->feat_cols) && (dxyz == nullptr || centre_src != nullptr),
               "pn2_mlp_dgrad: SCATTER targets inconsistent");
   g.G = *gather; g.dfeat = dfeat; g.ldf = ldf; g.dxyz = dxyz; g.centre_src = centre_src;
+  // without a coordinate gradient the xyz block (the last 4 columns) is never consumed: do not compute it
+  // (for 256 / 512 feature channels that is a whole extra 128-column tile)
+  if (dxyz == nullptr && gather->feat_cols > 0) g.N = gather->feat_cols;
+  if (dfeat == nullptr && dxyz == nullptr) return PN2_OK;
   if (wt != nullptr && gemm_tc_enabled()) {
     GemmArgs t2 = g;
-    t2.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+    t2.B = plain_rows(wt, g.N, dy->cols, dy->cols);
     const int rc = gemm_tc_launch(dy->kind, EPI_SCATTER, &t2, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
