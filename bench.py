@@ -167,6 +167,7 @@ def main_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PN2_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
     import _pn2
     from backbone import Pointnet2Backbone
