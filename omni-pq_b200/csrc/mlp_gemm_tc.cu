@@ -37,7 +37,7 @@ constexpr int TC_ROWS_PER_THREAD = TM * TC_CPR / TC_THREADS;     // chunk slots 
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 8 KB per operand half
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_KMAX = 640;                         // largest K whose per-channel coefficients are staged (plain form)
+constexpr int TC_KMAX = 1056;                        // largest K whose per-channel coefficients are staged (plain form)
 constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over K (or over 128 tile channels); B: 2 x 128
 constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
 constexpr uint32_t TMEM_COLS = 128;
