@@ -26,18 +26,13 @@ namespace {
 
 using namespace sm100;
 
-// CTA tile 128 x 128, k-blocks of 16 fp32 (64-byte swizzle rows).  The small k-block keeps a 3-stage ring at
-// 96 KB so that TWO CTAs (2 x 8 warps) share an SM: while one is in its prologue (TMEM allocation, first load
-// latency), at a barrier or draining its accumulator, the other one feeds the tensor pipe.  With one 16-warp
-// CTA per SM those phases were exposed (profiles/r1_ncu_gemm_tc_v3: tensor pipe 18 % busy).
-constexpr int TM = 128, TN = 128, TK = 16;
-constexpr int TC_THREADS = 256;
-constexpr int TC_CPR = TK / 4;                                   // 16-byte chunks per operand k-row
-constexpr int TC_ROWS_PER_THREAD = TM * TC_CPR / TC_THREADS;     // chunk slots of an operand k-block per thread (2)
+constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
+constexpr int TC_THREADS = 512;                    // 16 warps: latency hiding for the producers / epilogue
+constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
 constexpr int TC_STAGES = 3;
-constexpr int TILE_BYTES = TM * TK * 4;             // 8 KB per operand half
+constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_KMAX = 1056;                        // largest K whose per-channel coefficients are staged (plain form)
+constexpr int TC_KMAX = 1152;                        // largest K of the non-transposed form (coefficient staging)
 constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over K (or over 128 tile channels); B: 2 x 128
 constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
 constexpr uint32_t TMEM_COLS = 128;
@@ -117,7 +112,7 @@ __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int c
 // Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
 // 128-bit access touches 4 lines instead of 32.
 template <int AKIND, int BKIND, bool TRANS, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -147,22 +142,21 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const int coef_base_a = TRANS ? m0 : 0, coef_base_b = TRANS ? n0 : 0;
 
   // ---- producer mapping --------------------------------------------------------------------------------
-  // plain form : chunk = tid % 4 (16 bytes of the 64-byte k-row), rows rsub + 64*i (i < 2) of the A / B tile
+  // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 64*i (i < 2) of the A / B tile
   // transposed : lane = 16-byte channel quad of the tile's 128 channels (a warp reads one position's 512
-  //              contiguous bytes), positions warp + 8*i (i < 2) of the k-block, stored MN-major:
-  //              offset(k, q) = (q/8)*(TK*128) + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
+  //              contiguous bytes), positions warp + 16*i (i < 2) of the k-block, stored MN-major:
+  //              offset(k, q) = (q/8)*4096 + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
   constexpr int R = TC_ROWS_PER_THREAD;
-  constexpr int kWarps = TC_THREADS / 32;
-  const int chunk = tid % TC_CPR, rsub = tid / TC_CPR;
+  const int chunk = tid & 7, rsub = tid >> 3;
   uint32_t off[R];
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     if (!TRANS) {
-      off[i] = sw64_offset(rsub + (TC_THREADS / TC_CPR) * i, chunk);
+      off[i] = sw128_offset(rsub + 64 * i, chunk);
     } else {
-      const int k = warp + kWarps * i;
-      off[i] = static_cast<uint32_t>((lane >> 3) * (TK * 128) + (k >> 2) * 512 + (k & 3) * 128 +
-                                     ((((lane & 7) >> 1) ^ (k & 3)) << 5) + (lane & 1) * 16);
+      const int k = warp + 16 * i;
+      off[i] = static_cast<uint32_t>((lane >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((lane & 7) >> 1) ^ (k & 3)) << 5) +
+                                     (lane & 1) * 16);
     }
   }
 
@@ -170,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   auto make_ctx = [&](int kb, RowCtx *xa, RowCtx *xb) {  // transposed form: this thread's positions in k-block kb
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      const int p = k_begin + kb * TK + warp + kWarps * i;
+      const int p = k_begin + kb * TK + warp + 16 * i;
       const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
       xa[i] = row_ctx<AKIND>(g.A, r);
       xb[i] = row_ctx<BKIND>(g.B, r);
@@ -181,8 +175,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   } else {
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + (TC_THREADS / TC_CPR) * i);
-      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + (TC_THREADS / TC_CPR) * i);
+      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 64 * i);
     }
   }
   auto col_a = [&](int kb) { return TRANS ? m0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
@@ -243,14 +237,14 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       const uint32_t base = smem_addr(st);
       uint64_t a_hi, a_lo, b_hi, b_lo, step;
       if (TRANS) {
-        a_hi = smem_desc_mn_sw128_32b(base, TK * 128, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, TK * 128, 512);
-        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, TK * 128, 512);
-        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, TK * 128, 512);
+        a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
+        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
+        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
         step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
       } else {
-        a_hi = smem_desc_sw64(base); a_lo = smem_desc_sw64(base + TILE_BYTES);
-        b_hi = smem_desc_sw64(base + 2 * TILE_BYTES); b_lo = smem_desc_sw64(base + 3 * TILE_BYTES);
-        step = 32 >> 4;    // +32 bytes per k-step inside the 64-byte swizzle row
+        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
       }
 #pragma unroll
       for (int ks = 0; ks < TK / 8; ++ks) {
@@ -274,110 +268,372 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   tc_fence_after_sync();
 
   // ---- epilogue -------------------------------------------------------------------------------------------
-  // warp w reads TMEM lanes 32*(w%4)..+31 (tile rows); warps 0-3 take columns 0-63, warps 4-7 columns 64-127.
-  // Each 32x32 chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit
-  // accesses both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
+  // 16 warps, one 32 x 32 chunk each: warp w reads TMEM lanes 32*(w%4)..+31 (tile rows), columns 32*(w/4)..+31.
+  // The chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit accesses
+  // both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
   float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
   const int rbase = m0 + (warp & 3) * 32;
   const int cq = lane & 7, rs = lane >> 3;
+  const int c_local = (warp >> 2) * 32;
+  const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
+  {
+    float v[32];
+    if (num_kb > 0) {
+      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+    } else {  // empty position slice of a split weight gradient: the accumulator was never written
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c_local = (warp >> 2) * 64 + cc * 32;
-    const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
-    {
-      float v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
-      } else {  // empty position slice of a split weight gradient: the accumulator was never written
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    __syncwarp();
-    const bool col_ok = col < g.N;
-    float4 sc = zero4(), sh = zero4();
-    if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
-      sc = ldg4(g.prev_scale + col);
-      sh = ldg4(g.prev_shift + col);
-    }
-    float4 s1 = zero4(), s2 = zero4();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = rs + 4 * i;
-      const int row = rbase + rr;
-      float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
-      if (row >= g.M || !col_ok) continue;
-      if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
-        const int cloud = row / (g.G.npoint * g.G.nsample);
-        const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
-        const int fc = g.G.feat_cols;
-        if (col < fc) {
-          if (g.dfeat) {
-            float *dst = g.dfeat + src * g.ldf + col;
-            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-          }
-        } else if (col == fc && g.dxyz && g.G.use_xyz) {
-          const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
-                      gz = __fdiv_rn(v.z, g.G.inv_scale);
-          float *dn = g.dxyz + src * 3;
-          atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
-          const int centre = row / g.G.nsample;
-          float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
-          atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  __syncwarp();
+  const bool col_ok = col < g.N;
+  float4 sc = zero4(), sh = zero4();
+  if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
+    sc = ldg4(g.prev_scale + col);
+    sh = ldg4(g.prev_shift + col);
+  }
+  float4 s1 = zero4(), s2 = zero4();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = rs + 4 * i;
+    const int row = rbase + rr;
+    float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
+    if (row >= g.M || !col_ok) continue;
+    if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
+      const int cloud = row / (g.G.npoint * g.G.nsample);
+      const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
+      const int fc = g.G.feat_cols;
+      if (col < fc) {
+        if (g.dfeat) {
+          float *dst = g.dfeat + src * g.ldf + col;
+          atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
         }
-        continue;
+      } else if (col == fc && g.dxyz && g.G.use_xyz) {
+        const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                    gz = __fdiv_rn(v.z, g.G.inv_scale);
+        float *dn = g.dxyz + src * 3;
+        atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+        const int centre = row / g.G.nsample;
+        float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+        atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
       }
-      float4 qv;
-      if (EPI == TC_EPI_DGRAD_MASK) {
-        const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
-        v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
-        v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
-        v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
-        v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
-        qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
-      } else {
-        qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-      }
-      *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
-      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-      s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+      continue;
     }
-    __syncwarp();
-    if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-      // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
+    float4 qv;
+    if (EPI == TC_EPI_DGRAD_MASK) {
+      const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+      v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+      v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+      v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+      v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+      qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
+    } else {
+      qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+    *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+  }
+  if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
+    // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-        s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+    for (int o = 8; o <= 16; o <<= 1) {
+      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+    }
+    if (lane < 8) {
+      *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
+      *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
+    }
+    __syncthreads();
+    if (tid < 128) {  // tid -> (column group h = tid/32: warps 4h..4h+3 hold its four row blocks, column l)
+      const int h = tid >> 5, l = tid & 31;
+      const int c = n0 + h * 32 + l;
+      if (c < g.stats_ld) {
+        const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
+        const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
+        float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + c;
+        dst[0] = a;
+        dst[g.stats_ld] = b;
       }
-      if (lane < 8) {
-        *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
-        *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
-      }
-      __syncthreads();
-      if (tid < 64) {  // tid -> (half h = tid/32 selects warps 4h..4h+3, column l)
-        const int h = tid >> 5, l = tid & 31;
-        const int c = n0 + h * 64 + cc * 32 + l;
-        if (c < g.stats_ld) {
-          const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
-          const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
-          float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + c;
-          dst[0] = a;
-          dst[g.stats_ld] = b;
-        }
-      }
-      __syncthreads();
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+// ---- persistent, warp-specialised variant for the forward / data-gradient GEMMs ---------------------------
+// These GEMMs have a huge M (positions) and a short K (128..1028), i.e. only 4..33 k-blocks per 128x128 tile:
+// with one tile per CTA the prologue (TMEM allocation, first load latency) and the epilogue (accumulator
+// drain, 64 KB of stores) are as long as the main loop and nothing overlaps them (profiles/r1_ncu_gemm_tc_v3).
+// Here one CTA per SM walks over tiles: warps 0-7 produce operand stages (and thread 0 issues the MMAs),
+// warps 8-11 drain accumulators.  Two TMEM accumulators (2 x 128 columns) let the tensor pipe and the
+// producers work on tile i+1 while the epilogue warps store tile i; the first k-block of the next tile is
+// prefetched across the tile boundary.
+constexpr int PT_PRODUCERS = 256, PT_EPILOGUE = 128, PT_THREADS = PT_PRODUCERS + PT_EPILOGUE;
+constexpr int PT_STAGES = 3;
+constexpr int PT_SCRATCH = 4 * 32 * 36 * 4;  // one 32x36 fp32 transpose tile per epilogue warp
+constexpr int PT_KMAX = 768;  // largest K whose per-channel coefficients fit next to 3 stages (else: one-tile kernel)
+constexpr int PT_SMEM = PT_STAGES * STAGE_BYTES + 1024 + 256 + 3 * PT_KMAX * 4 + PT_SCRATCH;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+template <int AKIND, int EPI>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + PT_STAGES * STAGE_BYTES);  // [PT_STAGES]
+  uint64_t *acc_full = empty_bar + PT_STAGES;                                           // [2]
+  uint64_t *acc_empty = acc_full + 2;                                                   // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  float *coef_a = reinterpret_cast<float *>(tiles + PT_STAGES * STAGE_BYTES + 256);     // [3][PT_KMAX]
+  float *scratch = coef_a + 3 * PT_KMAX;
+  __shared__ float red[2][4][128];  // per-epilogue-warp column partials of one tile
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntn = (g.N + TN - 1) / TN;
+  const int ntiles = ((g.M + TM - 1) / TM) * ntn;
+  const int num_kb = (g.K + TK - 1) / TK;
+
+  if (tid == 0) {
+    for (int s = 0; s < PT_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  stage_coef<AKIND>(g.A, coef_a, PT_KMAX, 0, min(g.K, PT_KMAX), tid, PT_THREADS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(TM, TN);
+
+  if (warp < PT_PRODUCERS / 32) {
+    // ================= producers (+ MMA issue by thread 0) =================
+    const int chunk = tid & 7, rsub = tid >> 3;  // rows rsub + 32*i, i < 4
+    uint32_t off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) off[i] = sw128_offset(rsub + 32 * i, chunk);
+    RowCtx ca[4], cb[4];
+    Raw ra[4], rb[4];
+    int t = blockIdx.x;
+    auto tile_ctx = [&](int tile, RowCtx (&xa)[4], RowCtx (&xb)[4]) {
+      const int m0 = (tile / ntn) * TM, n0 = (tile % ntn) * TN;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xa[i] = row_ctx<AKIND>(g.A, tile < ntiles ? m0 + rsub + 32 * i : 0x7fffffff);
+        xb[i] = row_ctx<PN2_ROWS_PLAIN>(g.B, tile < ntiles ? n0 + rsub + 32 * i : 0x7fffffff);
+      }
+    };
+    tile_ctx(t, ca, cb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = fetch_raw<AKIND>(g.A, ca[i], chunk * 4);
+      rb[i] = fetch_raw<PN2_ROWS_PLAIN>(g.B, cb[i], chunk * 4);
+    }
+    int it = 0;  // k-blocks staged so far by this CTA (stage ring position)
+    for (int ti = 0; t < ntiles; ++ti, t += gridDim.x) {
+      const int buf = ti & 1;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % PT_STAGES;
+        // 1. next k-block's loads in flight (the next tile's first block when this is the tile's last one)
+        const bool last = kb + 1 == num_kb;
+        RowCtx na[4], nb[4];
+        Raw ra_next[4], rb_next[4];
+        if (last) tile_ctx(t + gridDim.x, na, nb);
+        const int kcol = (last ? 0 : (kb + 1) * TK) + chunk * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ra_next[i] = fetch_raw<AKIND>(g.A, last ? na[i] : ca[i], kcol);
+          rb_next[i] = fetch_raw<PN2_ROWS_PLAIN>(g.B, last ? nb[i] : cb[i], kcol);
+        }
+        // 2. wait until the MMAs that read this stage have completed
+        if (it >= PT_STAGES) mbar_wait(&empty_bar[s], ((it / PT_STAGES) - 1) & 1);
+        unsigned char *st = tiles + s * STAGE_BYTES;
+        // 3. transform + split + store
+        const int kc = kb * TK + chunk * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 va = apply_raw<AKIND>(g.A, ca[i], kc, ra[i], coef_a, PT_KMAX, 0);
+          const float4 vb = apply_raw<PN2_ROWS_PLAIN>(g.B, cb[i], kc, rb[i], coef_a, PT_KMAX, 0);
+          float4 hi, lo;
+          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
+          split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+          split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, PT_PRODUCERS);
+        if (tid == 0) {
+          if (kb == 0 && ti >= 2) mbar_wait(&acc_empty[buf], ((ti >> 1) - 1) & 1);  // epilogue drained this accumulator
+          tc_fence_after_sync();
+          const uint32_t base = smem_addr(st);
+          const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + TILE_BYTES);
+          const uint64_t b_hi = smem_desc_sw128(base + 2 * TILE_BYTES), b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+          const uint32_t d = tmem_base + buf * 128;
+#pragma unroll
+          for (int ks = 0; ks < TK / 8; ++ks) {
+            const uint64_t adv = static_cast<uint64_t>(2 * ks);
+            mma_tf32(d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+            mma_tf32(d, a_hi + adv, b_lo + adv, idesc, true);
+            mma_tf32(d, a_lo + adv, b_hi + adv, idesc, true);
+          }
+          mma_commit(&empty_bar[s]);
+          if (last) mma_commit(&acc_full[buf]);
+        }
+        // 4. rotate
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ra[i] = ra_next[i];
+          rb[i] = rb_next[i];
+          if (last) { ca[i] = na[i]; cb[i] = nb[i]; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int ew = warp - PT_PRODUCERS / 32;  // 0..3 = TMEM lane quarter = 32-row block of the tile
+    const int etid = tid - PT_PRODUCERS;
+    float *wt_tile = scratch + ew * (32 * 36);
+    const int cq = lane & 7, rs = lane >> 3;
+    int ti = 0;
+    for (int t = blockIdx.x; t < ntiles; ++ti, t += gridDim.x) {
+      const int buf = ti & 1;
+      const int m0 = (t / ntn) * TM, n0 = (t % ntn) * TN;
+      const int rbase = m0 + ew * 32;
+      mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c_local = cc * 32;
+        const int col = n0 + c_local + cq * 4;
+        {
+          float v[32];
+          tmem_ld32(tmem_base + buf * 128 + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(c_local), v);
+          if (cc == 3) {  // accumulator fully read: hand it back to the MMA issuer
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        const bool col_ok = col < g.N;
+        float4 sc = zero4(), sh = zero4();
+        if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
+          sc = ldg4(g.prev_scale + col);
+          sh = ldg4(g.prev_shift + col);
+        }
+        float4 s1 = zero4(), s2 = zero4();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rs + 4 * i;
+          const int row = rbase + rr;
+          float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
+          if (row >= g.M || !col_ok) continue;
+          if (EPI == TC_EPI_SCATTER) {
+            const int cloud = row / (g.G.npoint * g.G.nsample);
+            const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
+            const int fc = g.G.feat_cols;
+            if (col < fc) {
+              if (g.dfeat) {
+                float *dst = g.dfeat + src * g.ldf + col;
+                atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+              }
+            } else if (col == fc && g.dxyz && g.G.use_xyz) {
+              const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                          gz = __fdiv_rn(v.z, g.G.inv_scale);
+              float *dn = g.dxyz + src * 3;
+              atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+              const int centre = row / g.G.nsample;
+              float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+              atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+            }
+            continue;
+          }
+          float4 qv;
+          if (EPI == TC_EPI_DGRAD_MASK) {
+            const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+            v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+            v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+            v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+            v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+            qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
+          } else {
+            qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+          }
+          *reinterpret_cast<float4 *>(g.out + static_cast<size_t>(row) * g.ldo + col) = v;
+          s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+          s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+        }
+        __syncwarp();
+        if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+          }
+          if (lane < 8) {
+            *reinterpret_cast<float4 *>(&red[0][ew][c_local + cq * 4]) = s1;
+            *reinterpret_cast<float4 *>(&red[1][ew][c_local + cq * 4]) = s2;
+          }
+        }
+      }
+      if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
+        named_bar_sync(2, PT_EPILOGUE);
+        const int c = n0 + etid;  // one column per epilogue thread
+        if (c < g.stats_ld) {
+          const float a = red[0][0][etid] + red[0][1][etid] + red[0][2][etid] + red[0][3][etid];
+          const float b = red[1][0][etid] + red[1][1][etid] + red[1][2][etid] + red[1][3][etid];
+          float *dst = g.stats + static_cast<size_t>(t / ntn) * 2 * g.stats_ld + c;
+          dst[0] = a;
+          dst[g.stats_ld] = b;
+        }
+        named_bar_sync(2, PT_EPILOGUE);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+template <int AKIND, int EPI>
+int launch_tc_persistent(const GemmArgs &g, cudaStream_t stream) {
+  auto kernel = gemm_tc_persistent_kernel<AKIND, EPI>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+    configured_dev = dev;
+  }
+  const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  kernel<<<grid, PT_THREADS, PT_SMEM, stream>>>(g);
+  return check_launch("gemm_tc_persistent_kernel");
 }
 
 template <int AKIND, int BKIND, bool TRANS, int EPI>
@@ -410,10 +666,19 @@ bool gemm_tc_enabled() {
 // rows, which is what pn2_mlp_tiles() reports while this path is enabled.
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
+  if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
+  // The persistent, warp-specialised variant is correct but measured slower than one tile per 512-thread CTA
+  // (profiles/r1_gemm_bench_*): with only 8 producer warps the operand staging, not the prologue/epilogue,
+  // becomes the bottleneck.  It stays selectable for experiments: PN2_TC_PERSISTENT=1.
+  static const bool persistent = [] {
+    const char *e = getenv("PN2_TC_PERSISTENT");
+    return e != nullptr && e[0] == '1';
+  }();
   const bool needs_coef = akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER;
-  if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || (needs_coef && g.K > TC_KMAX)) return PN2_TC_UNSUPPORTED;
-#define PN2_TC_CASE(AK, EP) \
-  if (akind == AK && epi == EP) return launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
+  const bool use_pt = persistent && !(needs_coef && g.K > PT_KMAX);
+#define PN2_TC_CASE(AK, EP)                                                   \
+  if (akind == AK && epi == EP)                                               \
+    return use_pt ? launch_tc_persistent<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)

@@ -92,20 +92,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) {
   return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
 }
 
-// K-major operand tile, 64-byte swizzle: rows of 64 B (16 tf32), 8-row atoms of 512 B (SBO); the 16-byte
-// chunk index (2 bits) is XORed with address bits [7,9) = (row / 2) % 4  (Swizzle<2,4,3>).
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(512 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
-  return d;
-}
-__device__ __forceinline__ uint32_t sw64_offset(int r, int c16) {
-  return static_cast<uint32_t>(r * 64 + ((c16 ^ ((r >> 1) & 3)) << 4));
-}
-
 // MN-major operand tile [k rows][128 contiguous MN elements], 128-byte swizzle: atoms of 32 MN elements
 // (128 B) x 8 k-rows = 1024 B; consecutive k-groups of an atom column are SBO = 1024 B apart, atom columns
 // LBO bytes apart (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
