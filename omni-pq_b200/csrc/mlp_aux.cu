@@ -59,14 +59,15 @@ to_channel_major_kernel(int c, int n, int stride, const float *__restrict__ src,
 }
 
 // ---- BatchNorm statistics ---------------------------------------------------------------------------
-// stats[tiles][2][np] fp32 partials -> fp64 totals.  Block = 32 channels x 32 tile lanes: lane ty walks
-// tiles ty, ty+32, ... (coalesced across the 32 channels), the 32 lane totals are combined in a fixed
+// stats[tiles][2][np] fp32 partials -> fp64 totals.  Block = 8 channels x 128 tile lanes: lane ty walks
+// tiles ty, ty+128, ... (one 32-byte sector per tile row), the lane totals are combined in a fixed
 // order through shared memory, so the result is deterministic.  Every thread with ty == 0 gets the totals.
-constexpr int kStatCh = 32, kStatLanes = 32;
+constexpr int kStatCh = 8, kStatLanes = 128;  // 8 channels x 128 tile lanes per CTA: np/8 CTAs share the reduction
 
 __device__ __forceinline__ void total_of(const float *stats, int tiles, int np, int ch, bool live, double &s1,
                                          double &s2) {
   __shared__ double red[2][kStatLanes][kStatCh];
+  __shared__ double red8[2][8][kStatCh];
   const int tx = threadIdx.x % kStatCh, ty = threadIdx.x / kStatCh;
   double a = 0.0, b = 0.0;
   if (live && stats) {
@@ -78,12 +79,23 @@ __device__ __forceinline__ void total_of(const float *stats, int tiles, int np, 
   red[0][ty][tx] = a;
   red[1][ty][tx] = b;
   __syncthreads();
+  if (ty < 8) {  // fixed-order two-level combine: 8 partial sums of 16 lanes each, then 8 -> 1
+    double pa = 0.0, pb = 0.0;
+#pragma unroll
+    for (int l = 0; l < kStatLanes / 8; ++l) {
+      pa += red[0][ty * (kStatLanes / 8) + l][tx];
+      pb += red[1][ty * (kStatLanes / 8) + l][tx];
+    }
+    red8[0][ty][tx] = pa;
+    red8[1][ty][tx] = pb;
+  }
+  __syncthreads();
   s1 = 0.0; s2 = 0.0;
   if (ty == 0) {
 #pragma unroll
-    for (int l = 0; l < kStatLanes; ++l) {
-      s1 += red[0][l][tx];
-      s2 += red[1][l][tx];
+    for (int l = 0; l < 8; ++l) {
+      s1 += red8[0][l][tx];
+      s2 += red8[1][l][tx];
     }
   }
 }
@@ -206,7 +218,7 @@ bn_relu_pool_kernel(int groups, int group, int ld, const float *__restrict__ y, 
 }
 
 // gz = gout * (out > 0) in place; partial sums over a strip of groups of gz and gz * y[arg]
-constexpr int kPrepGroups = 32;  // groups per CTA strip
+constexpr int kPrepGroups = 8;  // groups per CTA strip
 
 __global__ void __launch_bounds__(128)
 pool_bwd_prep_kernel(int groups, int group, int ld, float *__restrict__ gz, const float *__restrict__ out_pm,
