@@ -170,8 +170,11 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       xb[i] = row_ctx<BKIND>(g.B, r);
     }
   };
+  RowCtx na[R], nb[R];  // transposed form: contexts of the NEXT k-block, resolved one block ahead of its loads so
+                        // that a gather's index load and the row loads that depend on it sit in different iterations
   if (TRANS) {
     make_ctx(0, ca, cb);
+    make_ctx(1, na, nb);
   } else {
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -202,9 +205,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
-    // 1. put the next k-block's loads in flight
-    RowCtx na[R], nb[R];
-    if (TRANS) make_ctx(kb + 1, na, nb);
+    // 1. put the next k-block's loads in flight, then resolve the contexts of the block after it
     if (kb + 1 < num_kb) {
 #pragma unroll
       for (int i = 0; i < R; ++i) {
@@ -263,6 +264,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
       rb[i] = rb_next[i];
       if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
     }
+    if (TRANS) make_ctx(kb + 2, na, nb);
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
