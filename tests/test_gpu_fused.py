@@ -323,3 +323,70 @@ def test_ffma_kernel_path_still_green():
                         "gemm or transposes or config1 or three_layer or without_features or fp_matches"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_config3_callers_vote_aggregation_and_fps_module_batch8(K, O):
+    """BASELINE.json configs[2] exercises the path through the detector's callers: FPSModule
+    (models/utils/pointnet_util.py:52-69 = furthest_point_sample + two gather_operations) and
+    vote_aggregation = PointnetSAModuleVotes(256, 0.3, 16, [288+3,288,288,288]) (models/pq_transformer.py:159-166)
+    on a batch of 8 clouds of 1024 seeds, eval mode (BN running statistics), xyz carrying gradients."""
+    import pointnet2_modules as M
+    import pointnet2_utils as U
+    kw = dict(npoint=256, radius=0.3, nsample=16, use_xyz=True, normalize_xyz=True)
+    ours, oracle = _pair(lambda: M.PointnetSAModuleVotes(mlp=[288, 288, 288, 288], **kw),
+                         lambda: O.OracleSAModuleVotes(mlp=[288, 288, 288, 288], **kw), seed=3, randomise_bn=True)
+    xyz, feats = O.uniform_cloud(8, 1024, 288, seed=31)
+    xyz = xyz * 0.9
+    # FPSModule
+    inds = U.furthest_point_sample(xyz.cuda(), 256)
+    inds_o = O.furthest_point_sample(xyz, 256)
+    assert torch.equal(inds.cpu(), inds_o)
+    g_xyz = U.gather_operation(xyz.cuda().transpose(1, 2).contiguous(), inds)
+    g_feat = U.gather_operation(feats.cuda(), inds)
+    assert torch.equal(g_xyz.cpu(), O.gather_operation(xyz.transpose(1, 2).contiguous(), inds_o))
+    assert torch.equal(g_feat.cpu(), O.gather_operation(feats, inds_o))
+    for train in (False, True):
+        ours.train(train)
+        oracle.train(train)
+        x_d, x_c = xyz.cuda().requires_grad_(True), xyz.clone().requires_grad_(True)
+        f_d, f_c = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True)
+        nx, out, ii = ours(x_d, f_d)
+        nx_o, out_o, ii_o = oracle(x_c, f_c)
+        assert torch.equal(ii.cpu(), ii_o) and torch.equal(nx.cpu(), nx_o)
+        assert rel(out, out_o) <= (FEAT_TOL if not train else 2 * FEAT_TOL), (train, rel(out, out_o))
+        cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(5))
+        (out * cot.cuda()).sum().backward()
+        (out_o * cot).sum().backward()
+        assert rel_l2(f_d.grad, f_c.grad) <= 1e-3 and rel_l2(x_d.grad, x_c.grad) <= 1e-3
+        for (n1, p1), (_, p2) in zip(ours.named_parameters(), oracle.named_parameters()):
+            assert rel_l2(p1.grad, p2.grad) <= 1e-3, (train, n1, rel_l2(p1.grad, p2.grad))
+        ours.zero_grad()
+        oracle.zero_grad()
+
+
+def test_config5_arkit_fp_stress(K, O):
+    """BASELINE.json configs[4]: ARKit-shaped 50000-point cloud (centred, yawed: points near the origin exercise
+    the FPS skip), PointnetFPModule(mlp=[256+3,256,128]) from SA1's 2048 points to all 50000, fwd+bwd."""
+    import pointnet2_modules as M
+    cloud = O.scannet_like_cloud(50000, seed=4321, centred=True, yaw=True)
+    xyz = cloud[None, :, :3].contiguous()
+    col = cloud[None, :, 3:].transpose(1, 2).contiguous()
+    inds_o = O.furthest_point_sample(xyz, 2048)
+    inds = K.furthest_point_sampling(xyz.cuda(), 2048)
+    assert torch.equal(inds.cpu(), inds_o)
+    known = torch.gather(xyz, 1, inds_o.long()[..., None].expand(-1, -1, 3)).contiguous()
+    kf = torch.randn(1, 256, 2048, generator=torch.Generator().manual_seed(8))
+    ours, oracle = _pair(lambda: M.PointnetFPModule(mlp=[256 + 3, 256, 128]), lambda: O.OracleFPModule(mlp=[256 + 3, 256, 128]), seed=9)
+    ours.train()
+    oracle.train()
+    c_d, k_d = col.cuda().requires_grad_(True), kf.cuda().requires_grad_(True)
+    c_c, k_c = col.clone().requires_grad_(True), kf.clone().requires_grad_(True)
+    out = ours(xyz.cuda(), known.cuda(), c_d, k_d)
+    out_o = oracle(xyz, known, c_c, k_c)
+    assert rel(out, out_o) <= FEAT_TOL, rel(out, out_o)
+    cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(6))
+    (out * cot.cuda()).sum().backward()
+    (out_o * cot).sum().backward()
+    assert rel_l2(c_d.grad, c_c.grad) <= 1e-3 and rel_l2(k_d.grad, k_c.grad) <= 1e-3
+    for (n1, p1), (_, p2) in zip(ours.named_parameters(), oracle.named_parameters()):
+        assert rel_l2(p1.grad, p2.grad) <= 1e-3, (n1, rel_l2(p1.grad, p2.grad))
