@@ -23,6 +23,7 @@
 //     (bitrev(k mod bs), k div bs) -- encoded below as `rank`; bs = pn2_ref_block_size(n);
 //   * if no point is a candidate (all skipped) the reference yields index 0.
 #include <limits.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -324,6 +325,219 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
   if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
 }
 
+// ---- register-resident kernel, several picks per exchange round ----------------------------------------------
+// The chain above pays one block + cluster exchange (~1300 cycles) per sampled point.  Most of those
+// exchanges are avoidable without changing a single output bit:
+//
+//   After a round, let C be a set of candidate points whose current min-distances are known to every warp
+//   (with coordinates), and let `bmax` bound the min-distance of every point NOT in C.  Min-distances only
+//   decrease, so `bmax` stays a bound while further points are picked.  The next sample is the arg-max over
+//   all points; if, after updating the candidates with the picks made so far, the best candidate's distance
+//   is strictly above `bmax`, no outsider can beat or tie it, and it IS the reference's next pick (ties
+//   between candidates are resolved with the reference rank).  Otherwise the round ends and the next
+//   exchange recomputes exact candidates; its first pick is always the exact global arg-max.
+//
+// Candidates: per warp the exact arg-max (total order: distance, then reference rank) plus the value of the
+// best OTHER point of the warp (thread-level runner-up / other lanes' maxima) as that warp's bound.  With a
+// cluster, each CTA forwards its two best warp candidates and max(third candidate, warp bounds) to every
+// CTA: 32 candidates, one per lane.  Every warp then resolves picks redundantly (identical arithmetic:
+// dist2(candidate, pick) is the same expression its owner thread evaluates in the next round), and the
+// next round applies all picks of the previous one to the register-resident points.
+// On a 40k-point room scan this makes ~9 picks per exchange (2047 rounds -> ~230).
+template <int NW>
+struct alignas(16) FpsSmem4 {
+  uint4 wcand[2][NW];                  // per-warp candidate {key, k, x bits, y bits}
+  uint4 ccand[2][2 * kFpsMaxCluster];  // [c]: best of CTA c, [16 + c]: its runner-up
+  float wz[2][NW];
+  int wbound[2][NW];                   // best key among the warp's points other than its candidate
+  float cz[2][2 * kFpsMaxCluster];
+  int cbound[2][kFpsMaxCluster];       // bound over the CTA's points other than its two candidates
+  unsigned long long bar[2];
+};
+constexpr uint32_t kCand2Bytes = 44;   // best: v4 + z + bound, runner-up: v4 + z
+
+// order-preserving int key of a min-distance: >= 0 -> float bits, "never a candidate" (-1) -> -1
+__device__ __forceinline__ int fps_key(float v) { return v < 0.f ? -1 : __float_as_int(v); }
+
+template <int PTS>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
+                     int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  constexpr int NW = kFpsThreads / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FpsSmem4<NW> &S = *reinterpret_cast<FpsSmem4<NW> *>(smem_raw);
+  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem4<NW>));
+  float *sy = sx + PTS * kFpsThreads;
+  float *sz = sy + PTS * kFpsThreads;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
+  const int batch = blockIdx.x / cs;
+  xyz += static_cast<size_t>(batch) * n * 3;
+  idxs += static_cast<size_t>(batch) * m;
+  if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
+  const int T = cs * kFpsThreads;
+  const int g = static_cast<int>(my_cta) * kFpsThreads + tid;
+
+  float px[PTS], py[PTS], pz[PTS], pt[PTS];
+#pragma unroll
+  for (int i = 0; i < PTS; ++i) {
+    const int k = g + i * T;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool valid = false;
+    if (k < n) {
+      x = xyz[k * 3 + 0];
+      y = xyz[k * 3 + 1];
+      z = xyz[k * 3 + 2];
+      valid = !(static_cast<double>(sq3(x, y, z)) <= 1e-3);  // sampling_gpu.cu:105-106
+    }
+    px[i] = x; py[i] = y; pz[i] = z;
+    pt[i] = valid ? 1e10f : -1.0f;  // -1: never a candidate, fminf keeps it at -1
+    sx[i * kFpsThreads + tid] = x;
+    sy[i * kFpsThreads + tid] = y;
+    sz[i * kFpsThreads + tid] = z;
+  }
+  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
+  if (g == 0) {
+    idxs[0] = 0;
+    if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
+  }
+  if (cs > 1) {
+    if (tid == 0) {
+      mbar_init(&S.bar[0], 1);
+      mbar_init(&S.bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_arrive_expect_tx(&S.bar[0], cs * kCand2Bytes);
+      mbar_arrive_expect_tx(&S.bar[1], cs * kCand2Bytes);
+    }
+    cluster_sync_all();
+  }
+
+  // picks of the previous round, not yet applied to the resident points: lane q < npend holds pick q
+  float qx = x0, qy = y0, qz = z0;
+  int npend = 1;
+  int j = 1;  // next output slot
+  for (int round = 0; j < m; ++round) {
+    const int p = round & 1;
+    // ---- apply the pending picks, then the thread's best / runner-up ----
+#pragma unroll 1
+    for (int q = 0; q < npend; ++q) {
+      const float xq = __shfl_sync(FULL, qx, q), yq = __shfl_sync(FULL, qy, q), zq = __shfl_sync(FULL, qz, q);
+#pragma unroll
+      for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], xq, yq, zq), pt[i]);
+    }
+    float best = -2.0f, second = -2.0f;
+    int ib = 0;
+#pragma unroll
+    for (int i = 0; i < PTS; ++i) {
+      const float t = pt[i];
+      if (t > best) { second = best; best = t; ib = i; }  // strict '>': lowest i (lowest rank in the thread) wins ties
+      else second = fmaxf(second, t);
+    }
+    // ---- warp level: exact arg-max + bound over the warp's other points ----
+    const int kb = fps_key(best), ks = fps_key(second);
+    const int kmine = g + ib * T;
+    {
+      const int src = warp_argmax_lane(kb, kmine, true, bs_log2);
+      const int wb = __reduce_max_sync(FULL, lane == src ? ks : kb);
+      if (lane == src) {
+        const int slot = ib * kFpsThreads + tid;
+        S.wcand[p][warp] = make_uint4(static_cast<uint32_t>(kb), static_cast<uint32_t>(kmine), __float_as_uint(sx[slot]),
+                                      __float_as_uint(sy[slot]));
+        S.wz[p][warp] = sz[slot];
+        S.wbound[p][warp] = wb;
+      }
+    }
+    __syncthreads();
+    // ---- candidates of this round, one per lane ----
+    int cd = INT_MIN, ck = 0, bmax;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    bool valid;
+    if (cs == 1) {
+      valid = lane < NW;
+      int wb = INT_MIN;
+      if (valid) {
+        const uint4 e = S.wcand[p][lane];
+        cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
+        cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.wz[p][lane];
+        wb = S.wbound[p][lane];
+      }
+      bmax = __reduce_max_sync(FULL, wb);
+    } else {
+      if (warp < 2) {  // warp 0 forwards the CTA's best warp candidate (+ bound), warp 1 the runner-up
+        int d = INT_MIN, k = 0, wb = INT_MIN;
+        if (lane < NW) {
+          const uint4 e = S.wcand[p][lane];
+          d = static_cast<int>(e.x); k = static_cast<int>(e.y);
+          wb = S.wbound[p][lane];
+        }
+        const int src1 = warp_argmax_lane(d, k, lane < NW, bs_log2);
+        const bool rest = lane < NW && lane != src1;
+        const int m2 = __reduce_max_sync(FULL, rest ? d : INT_MIN);
+        const int src2 = __ffs(__ballot_sync(FULL, rest && d == m2)) - 1;
+        if (warp == 0) {
+          const int third = __reduce_max_sync(FULL, (rest && lane != src2) ? d : INT_MIN);
+          const int cb = max(third, __reduce_max_sync(FULL, wb));
+          if (lane < cs) {
+            const uint4 w = S.wcand[p][src1];
+            const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+            st_async_v4(mapa_u32(smem_u32(&S.ccand[p][my_cta]), lane), rbar, w.x, w.y, w.z, w.w);
+            st_async_b32(mapa_u32(smem_u32(&S.cz[p][my_cta]), lane), rbar, __float_as_uint(S.wz[p][src1]));
+            st_async_b32(mapa_u32(smem_u32(&S.cbound[p][my_cta]), lane), rbar, static_cast<uint32_t>(cb));
+          }
+        } else if (lane < cs) {
+          const uint4 w = S.wcand[p][src2];
+          const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+          st_async_v4(mapa_u32(smem_u32(&S.ccand[p][kFpsMaxCluster + my_cta]), lane), rbar, w.x, w.y, w.z, w.w);
+          st_async_b32(mapa_u32(smem_u32(&S.cz[p][kFpsMaxCluster + my_cta]), lane), rbar, __float_as_uint(S.wz[p][src2]));
+        }
+      }
+      mbar_wait(&S.bar[p], (round >> 1) & 1);
+      if (tid == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCand2Bytes);  // re-arm for round + 2
+      valid = (lane & (kFpsMaxCluster - 1)) < cs;
+      if (valid) {
+        const uint4 e = S.ccand[p][lane];
+        cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
+        cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.cz[p][lane];
+      }
+      bmax = __reduce_max_sync(FULL, lane < cs ? S.cbound[p][lane] : INT_MIN);
+    }
+    // ---- resolve as many picks as the bound allows (every warp, identical result) ----
+    int npick = 0;
+    while (true) {
+      const int src = warp_argmax_lane(cd, ck, valid, bs_log2);
+      const int dbest = __shfl_sync(FULL, cd, src);
+      if (npick == 0) {
+        if (dbest < 0) {  // no point is a candidate: the reference yields index 0 from here on
+          if (g == 0)
+            for (int t = j; t < m; ++t) {
+              idxs[t] = 0;
+              if (new_xyz) { new_xyz[t * 3 + 0] = x0; new_xyz[t * 3 + 1] = y0; new_xyz[t * 3 + 2] = z0; }
+            }
+          npick = m - j;
+          break;
+        }
+      } else if (dbest <= bmax) {
+        break;  // an outsider may beat or tie it: exact candidates are needed
+      }
+      const int kq = __shfl_sync(FULL, ck, src);
+      const float xq = __shfl_sync(FULL, cx, src), yq = __shfl_sync(FULL, cy, src), zq = __shfl_sync(FULL, cz, src);
+      if (g == 0) {
+        idxs[j + npick] = kq;
+        if (new_xyz) { new_xyz[(j + npick) * 3 + 0] = xq; new_xyz[(j + npick) * 3 + 1] = yq; new_xyz[(j + npick) * 3 + 2] = zq; }
+      }
+      if (lane == npick) { qx = xq; qy = yq; qz = zq; }
+      ++npick;
+      if (j + npick >= m || npick == 32) break;
+      if (valid && cd >= 0) cd = __float_as_int(fminf(dist2(cx, cy, cz, xq, yq, zq), __int_as_float(cd)));
+    }
+    j += npick;
+    npend = npick < 32 ? npick : 32;
+  }
+  if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
+}
+
 // ---- streaming fallback (n beyond register capacity): same exchange, points from L2 ---------------
 __global__ void __launch_bounds__(kStreamThreads, 1)
 fps_streaming_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
@@ -423,8 +637,32 @@ int launch_cluster(K kernel, int grid, int block, size_t smem, int cs, cudaStrea
 }
 
 template <int PTS>
+int launch_multipick(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
+                     cudaStream_t stream) {
+  auto kernel = fps_multipick_kernel<PTS>;
+  const size_t smem = sizeof(FpsSmem4<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
+  static thread_local int configured_dev = -1;
+  if (!configured_on(configured_dev)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
+  void *args[] = {&n, &m, &cs, &bs_log2, &xyz, &idxs, &new_xyz};
+  return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
+}
+
+// PN2_FPS_MULTIPICK=0 selects the one-pick-per-round kernel (A/B measurements)
+bool fps_multipick_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("PN2_FPS_MULTIPICK");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+template <int PTS>
 int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
                     cudaStream_t stream) {
+  if (fps_multipick_enabled()) return launch_multipick<PTS>(b, n, m, cs, bs_log2, xyz, idxs, new_xyz, stream);
   auto kernel = fps_resident_kernel<PTS>;
   const size_t smem = sizeof(FpsSmem2<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
   static thread_local int configured_dev = -1;
