@@ -133,7 +133,12 @@ typedef struct pn2_rows {
 /* Weights (cout,cin) row-major -> zero padded, optionally column-permuted copies used by the GEMMs:
  * wt [kp][np] (k-major, for forward) and wp [np][kp] (for dgrad).  `xyz_first` != 0 moves the first three
  * input channels (the xyz channels QueryAndGroup puts first) behind the `feat_pad` feature channels so
- * that gathered feature rows stay 16-byte aligned: k' = [features 0..cin-4 | pad | x y z 0]. */
+ * that gathered feature rows stay 16-byte aligned: k' = [features 0..cin-4 | pad | x y z 0].
+ * Each buffer additionally carries, right after the plain matrix, the tensor-core image of that matrix
+ * (every 128-row x 32-column block split into tf32 hi / lo halves, in the UMMA 128-byte-swizzle layout) which the
+ * forward / dgrad kernels fetch with one bulk copy per k-block.  Sizes, in floats:
+ * wt: pn2_mlp_weight_floats(kp, np), wp: pn2_mlp_weight_floats(np, kp). */
+long long pn2_mlp_weight_floats(int rows, int cols);
 int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, const float *w,
                          float *wt, float *wp, void *stream);
 

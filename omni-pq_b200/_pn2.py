@@ -341,6 +341,8 @@ _pool_tiles = _sig("pn2_pool_bwd_tiles", _i, kernel=False)
 _bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
 _wgrad = _sig("pn2_mlp_wgrad", _rp, _rp, _i, _i, _i, _i, _vp, _vp, _vp)
+lib.pn2_mlp_weight_floats.argtypes = [_i, _i]
+lib.pn2_mlp_weight_floats.restype = ctypes.c_longlong
 lib.pn2_mlp_wgrad_workspace.argtypes = [_i, _i, _i]
 lib.pn2_mlp_wgrad_workspace.restype = ctypes.c_longlong
 _fp_interp = _sig("pn2_fp_interpolate", _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp)
@@ -360,7 +362,9 @@ def _f32(dev, *shape, zero=False):
 def mlp_prep_weights(w2d, xyz_first, feat_pad, kp, np_):
     """(cout,cin) weights -> (wt [kp,np], wp [np,kp]) padded / permuted copies."""
     cout, cin = w2d.shape
-    wt, wp = _f32(w2d.device, kp, np_), _f32(w2d.device, np_, kp)
+    # each buffer = plain matrix + its tensor-core image (pn2_b200.h); the returned tensors view the plain part
+    wt = _f32(w2d.device, lib.pn2_mlp_weight_floats(kp, np_))[:kp * np_].view(kp, np_)
+    wp = _f32(w2d.device, lib.pn2_mlp_weight_floats(np_, kp))[:kp * np_].view(np_, kp)
     _check(_prep(cout, cin, int(xyz_first), feat_pad, kp, np_, _ptr(w2d), _ptr(wt), _ptr(wp), _stream()))
     _launched()
     return wt, wp

@@ -265,19 +265,58 @@ __device__ __forceinline__ int orig_cin(int kq, int cin, int xyz_first, int feat
   return d < 3 ? d : -1;
 }
 
+// Tensor-core image of a K-major operand matrix B [rows][cols] (mlp_gemm_tc.cu, gemm_tc_bulk_kernel): for every
+// (128-row tile, 32-column k-block) one 32 KB stage = [hi 16 KB | lo 16 KB], each half in the UMMA K-major
+// 128-byte-swizzle layout (row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c XOR (r%8)), zero padded.
+constexpr int IMG_STAGE_FLOATS = 2 * 128 * 32;
+__host__ __device__ inline long long img_floats(int rows, int cols) {
+  return static_cast<long long>((rows + 127) / 128) * ((cols + 31) / 32) * IMG_STAGE_FLOATS;
+}
+__device__ __forceinline__ void img_store(float *img, int cols, long long e, float v) {
+  // e enumerates (tile, k-block, row-in-tile, col-in-block); returns through img the hi / lo placement
+  const int c = static_cast<int>(e & 31), r = static_cast<int>((e >> 5) & 127);
+  const long long stage = e >> 12;
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  const float hi = __uint_as_float(h), lo = v - hi;
+  const int off = (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));  // floats inside a 16 KB half
+  float *st = img + stage * IMG_STAGE_FLOATS;
+  st[off] = hi;
+  st[4096 + off] = lo;
+  (void)cols;
+}
+
 __global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np,
-                                    const float *__restrict__ w, float *__restrict__ wt, float *__restrict__ wp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kp * np) return;
-  {  // wt[k][n]
-    const int k = i / np, n = i % np;
-    const int c = orig_cin(k, cin, xyz_first, feat_pad);
-    wt[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+                                    const float *__restrict__ w, float *__restrict__ wt, float *__restrict__ wp,
+                                    long long img_t, long long img_p) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<long long>(kp) * np) {
+    {  // wt[k][n]
+      const int k = static_cast<int>(i / np), n = static_cast<int>(i % np);
+      const int c = orig_cin(k, cin, xyz_first, feat_pad);
+      wt[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+    }
+    {  // wp[n][k]
+      const int n = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
+      const int c = orig_cin(k, cin, xyz_first, feat_pad);
+      wp[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+    }
   }
-  {  // wp[n][k]
-    const int n = i / kp, k = i % kp;
-    const int c = orig_cin(k, cin, xyz_first, feat_pad);
-    wp[i] = (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f;
+  if (i < img_t) {  // image of wt: operand rows = k (kp of them), operand columns = n
+    const int nkb = (np + 31) / 32;
+    const long long stage = i >> 12;
+    const int k = static_cast<int>(stage / nkb) * 128 + static_cast<int>((i >> 5) & 127);
+    const int n = static_cast<int>(stage % nkb) * 32 + static_cast<int>(i & 31);
+    const int c = k < kp ? orig_cin(k, cin, xyz_first, feat_pad) : -1;
+    img_store(wt + static_cast<size_t>(kp) * np, np, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
+  }
+  if (i < img_p) {  // image of wp: operand rows = n, operand columns = k
+    const int nkb = (kp + 31) / 32;
+    const long long stage = i >> 12;
+    const int n = static_cast<int>(stage / nkb) * 128 + static_cast<int>((i >> 5) & 127);
+    const int k = static_cast<int>(stage % nkb) * 32 + static_cast<int>(i & 31);
+    const int c = k < kp ? orig_cin(k, cin, xyz_first, feat_pad) : -1;
+    img_store(wp + static_cast<size_t>(kp) * np, kp, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
   }
 }
 
@@ -319,15 +358,22 @@ int wgrad_splits(int rows, int np, int kp) {
 
 using namespace pn2;
 
+PN2_EXPORT long long pn2_mlp_weight_floats(int rows, int cols) {
+  return static_cast<long long>(rows) * cols + img_floats(rows, cols);
+}
+
 PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, const float *w,
                                     float *wt, float *wp, void *stream) {
   PN2_REQUIRE(cout > 0 && cin > 0 && kp >= 4 && np >= cout && (kp % 4) == 0 && (np % 4) == 0 && w && wt && wp,
               "pn2_mlp_prep_weights: bad arguments cout=%d cin=%d kp=%d np=%d", cout, cin, kp, np);
   PN2_REQUIRE(xyz_first ? (cin >= 3 && feat_pad >= cin - 3 && kp == feat_pad + 4) : kp >= cin,
               "pn2_mlp_prep_weights: inconsistent padding cin=%d feat_pad=%d kp=%d", cin, feat_pad, kp);
-  const int total = kp * np;
-  prep_weights_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(cout, cin, xyz_first, feat_pad,
-                                                                                       kp, np, w, wt, wp);
+  const long long img_t = img_floats(kp, np) / 2, img_p = img_floats(np, kp) / 2;  // one thread per (hi, lo) pair
+  long long total = static_cast<long long>(kp) * np;
+  if (img_t > total) total = img_t;
+  if (img_p > total) total = img_p;
+  prep_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p);
   return check_launch("pn2_mlp_prep_weights");
 }
 
@@ -356,6 +402,8 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
   if (wp != nullptr && gemm_tc_enabled()) {  // tensor-core path: B = W as [np][kp], K-major
     GemmArgs t = g;
     t.B = plain_rows(wp, np, kp, kp);
+    t.b_img = wp + static_cast<size_t>(np) * kp;
+    t.b_img_kblocks = (kp + 31) / 32;
     const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
@@ -393,6 +441,8 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
     if (tc) {  // B = W^T as [ncols][dy.cols], K-major: that is wt
       t = g;
       t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+      t.b_img = wt + static_cast<size_t>(ncols) * dy->cols;
+      t.b_img_kblocks = (dy->cols + 31) / 32;
       const int rc = gemm_tc_launch(dy->kind, EPI_DGRAD_MASK, &t, s);
       if (rc != PN2_TC_UNSUPPORTED) return rc;
     }
@@ -404,6 +454,8 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
     if (tc) {
       t = g;
       t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
+      t.b_img = wt + static_cast<size_t>(ncols) * dy->cols;
+      t.b_img_kblocks = (dy->cols + 31) / 32;
       const int rc = gemm_tc_launch(dy->kind, EPI_STORE, &t, s);
       if (rc != PN2_TC_UNSUPPORTED) return rc;
     }
@@ -425,6 +477,8 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
   if (wt != nullptr && gemm_tc_enabled()) {
     GemmArgs t2 = g;
     t2.B = plain_rows(wt, g.N, dy->cols, dy->cols);
+    t2.b_img = wt + static_cast<size_t>(ncols) * dy->cols;  // the image follows the full [ncols][dy.cols] matrix
+    t2.b_img_kblocks = (dy->cols + 31) / 32;
     const int rc = gemm_tc_launch(dy->kind, EPI_SCATTER, &t2, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }

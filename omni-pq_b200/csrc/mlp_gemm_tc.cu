@@ -102,6 +102,112 @@ __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int c
   }
 }
 
+// ---- epilogue (shared by the kernels below) ------------------------------------------------------------------
+// Drains the 128 x 128 fp32 accumulator at `tmem_d` of the tile at (m0, n0); `scratch` = the (now idle) operand
+// stages, `red` = per-warp column partials.  m_tile indexes the per-row-tile statistics, split the wgrad slice.
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, unsigned char *tiles,
+                                            float (&red)[2][TC_THREADS / 32][32], int m0, int n0, int m_tile, int split,
+                                            bool have_acc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // 16 warps, one 32 x 32 chunk each: warp w reads TMEM lanes 32*(w%4)..+31 (tile rows), columns 32*(w/4)..+31.
+  // The chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit accesses
+  // both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
+  float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
+  const int rbase = m0 + (warp & 3) * 32;
+  const int cq = lane & 7, rs = lane >> 3;
+  const int c_local = (warp >> 2) * 32;
+  const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
+  {
+    float v[32];
+    if (have_acc) {
+      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
+    } else {  // empty position slice of a split weight gradient: the accumulator was never written
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  __syncwarp();
+  const bool col_ok = col < g.N;
+  float4 sc = zero4(), sh = zero4();
+  if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
+    sc = ldg4(g.prev_scale + col);
+    sh = ldg4(g.prev_shift + col);
+  }
+  float4 s1 = zero4(), s2 = zero4();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = rs + 4 * i;
+    const int row = rbase + rr;
+    float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
+    if (row >= g.M || !col_ok) continue;
+    if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
+      const int cloud = row / (g.G.npoint * g.G.nsample);
+      const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
+      const int fc = g.G.feat_cols;
+      if (col < fc) {
+        if (g.dfeat) {
+          float *dst = g.dfeat + src * g.ldf + col;
+          atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+        }
+      } else if (col == fc && g.dxyz && g.G.use_xyz) {
+        const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
+                    gz = __fdiv_rn(v.z, g.G.inv_scale);
+        float *dn = g.dxyz + src * 3;
+        atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
+        const int centre = row / g.G.nsample;
+        float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
+        atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
+      }
+      continue;
+    }
+    float4 qv;
+    if (EPI == TC_EPI_DGRAD_MASK) {
+      const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+      v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
+      v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
+      v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
+      v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
+      qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
+    } else {
+      qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+    *reinterpret_cast<float4 *>(g.out + split * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
+  }
+  if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
+    // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+    }
+    if (lane < 8) {
+      *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
+      *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
+    }
+    __syncthreads();
+    if (tid < 128) {  // tid -> (column group h = tid/32: warps 4h..4h+3 hold its four row blocks, column l)
+      const int h = tid >> 5, l = tid & 31;
+      const int c = n0 + h * 32 + l;
+      if (c < g.stats_ld) {
+        const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
+        const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
+        float *dst = g.stats + static_cast<size_t>(m_tile) * 2 * g.stats_ld + c;
+        dst[0] = a;
+        dst[g.stats_ld] = b;
+      }
+    }
+  }
+
+}
+
 // TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory.
 // TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and B = activation source are both
 // position rows with channels contiguous.  They are transposed while they are staged into the same K-major
@@ -269,373 +375,184 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
 
-  // ---- epilogue -------------------------------------------------------------------------------------------
-  // 16 warps, one 32 x 32 chunk each: warp w reads TMEM lanes 32*(w%4)..+31 (tile rows), columns 32*(w/4)..+31.
-  // The chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit accesses
-  // both ways) so that global accesses are row-contiguous: lane -> (row rs + 4*i, 4 columns 4*cq..).
-  float *wt_tile = reinterpret_cast<float *>(tiles) + warp * (32 * 36);  // the operand stages are free now
-  const int rbase = m0 + (warp & 3) * 32;
-  const int cq = lane & 7, rs = lane >> 3;
-  const int c_local = (warp >> 2) * 32;
-  const int col = n0 + c_local + cq * 4;  // this lane's 4 columns
-  {
-    float v[32];
-    if (num_kb > 0) {
-      tmem_ld32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(c_local), v);
-    } else {  // empty position slice of a split weight gradient: the accumulator was never written
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  }
-  __syncwarp();
-  const bool col_ok = col < g.N;
-  float4 sc = zero4(), sh = zero4();
-  if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
-    sc = ldg4(g.prev_scale + col);
-    sh = ldg4(g.prev_shift + col);
-  }
-  float4 s1 = zero4(), s2 = zero4();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = rs + 4 * i;
-    const int row = rbase + rr;
-    float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
-    if (row >= g.M || !col_ok) continue;
-    if (EPI == TC_EPI_SCATTER) {  // transpose of the gather: scatter-add into the neighbour's feature row / xyz
-      const int cloud = row / (g.G.npoint * g.G.nsample);
-      const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
-      const int fc = g.G.feat_cols;
-      if (col < fc) {
-        if (g.dfeat) {
-          float *dst = g.dfeat + src * g.ldf + col;
-          atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-        }
-      } else if (col == fc && g.dxyz && g.G.use_xyz) {
-        const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
-                    gz = __fdiv_rn(v.z, g.G.inv_scale);
-        float *dn = g.dxyz + src * 3;
-        atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
-        const int centre = row / g.G.nsample;
-        float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
-        atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
-      }
-      continue;
-    }
-    float4 qv;
-    if (EPI == TC_EPI_DGRAD_MASK) {
-      const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
-      v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
-      v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
-      v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
-      v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
-      qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
-    } else {
-      qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-    }
-    *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(row) * g.ldo + col) = v;
-    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-    s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
-  }
-  if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-    // column totals of this warp's 32 rows: combine the 4 row groups (lanes l, l^8, l^16, l^24)
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
-    }
-    if (lane < 8) {
-      *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
-      *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
-    }
-    __syncthreads();
-    if (tid < 128) {  // tid -> (column group h = tid/32: warps 4h..4h+3 hold its four row blocks, column l)
-      const int h = tid >> 5, l = tid & 31;
-      const int c = n0 + h * 32 + l;
-      if (c < g.stats_ld) {
-        const float a = red[0][4 * h][l] + red[0][4 * h + 1][l] + red[0][4 * h + 2][l] + red[0][4 * h + 3][l];
-        const float b = red[1][4 * h][l] + red[1][4 * h + 1][l] + red[1][4 * h + 2][l] + red[1][4 * h + 3][l];
-        float *dst = g.stats + static_cast<size_t>(blockIdx.x) * 2 * g.stats_ld + c;
-        dst[0] = a;
-        dst[g.stats_ld] = b;
-      }
-    }
-  }
+  tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
-// ---- persistent, warp-specialised variant for the forward / data-gradient GEMMs ---------------------------
-// These GEMMs have a huge M (positions) and a short K (128..1028), i.e. only 4..33 k-blocks per 128x128 tile:
-// with one tile per CTA the prologue (TMEM allocation, first load latency) and the epilogue (accumulator
-// drain, 64 KB of stores) are as long as the main loop and nothing overlaps them (profiles/r1_ncu_gemm_tc_v3).
-// Here one CTA per SM walks over tiles: warps 0-7 produce operand stages (and thread 0 issues the MMAs),
-// warps 8-11 drain accumulators.  Two TMEM accumulators (2 x 128 columns) let the tensor pipe and the
-// producers work on tile i+1 while the epilogue warps store tile i; the first k-block of the next tile is
-// prefetched across the tile boundary.
-constexpr int PT_PRODUCERS = 256, PT_EPILOGUE = 128, PT_THREADS = PT_PRODUCERS + PT_EPILOGUE;
-constexpr int PT_STAGES = 3;
-constexpr int PT_SCRATCH = 4 * 32 * 36 * 4;  // one 32x36 fp32 transpose tile per epilogue warp
-constexpr int PT_KMAX = 768;  // largest K whose per-channel coefficients fit next to 3 stages (else: one-tile kernel)
-constexpr int PT_SMEM = PT_STAGES * STAGE_BYTES + 1024 + 256 + 3 * PT_KMAX * 4 + PT_SCRATCH;
+// ---- forward / data-gradient kernel with a bulk-copied weight operand ---------------------------------------
+// ncu of gemm_tc_kernel on the backbone's shapes (profiles/c1_ncu_gemm.json): the top stall is long_scoreboard
+// (global-load latency) at 16 resident warps -- one k-block of A and B in flight per thread is ~16 KB per SM,
+// far below what HBM needs.  For the non-transposed GEMMs B is the layer's weight matrix, identical for every
+// row tile, so its hi/lo split and 128-byte-swizzle layout are computed ONCE by pn2_mlp_prep_weights into an
+// image [n-tile][k-block][hi 16 KB | lo 16 KB]; here one thread fetches each 32 KB stage with a single
+// cp.async.bulk (complete_tx on a "full" mbarrier), two k-blocks ahead, into a 4-stage ring.  That removes half
+// of the staging instructions and the B registers, which pays for a second k-block of A prefetch per thread
+// (register sets: current, +1, +2, +3).  A: 2-stage ring written by all 16 warps as before.
+// Tiles are numbered with the n-tile fastest so that the CTAs sharing a row tile run together and the second
+// one reads A from L2.
+constexpr int BK_A_STAGES = 2, BK_B_STAGES = 4;
+constexpr int BK_A_BYTES = 2 * TILE_BYTES, BK_B_BYTES = 2 * TILE_BYTES;  // hi + lo
+constexpr int BK_RING = BK_A_STAGES * BK_A_BYTES + BK_B_STAGES * BK_B_BYTES;
+constexpr int BK_SMEM = BK_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
 
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// mbarrier wait that traps instead of hanging the GPU if a transaction count was ever wrong
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && (spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
 }
 
 template <int AKIND, int EPI>
-__global__ void __launch_bounds__(PT_THREADS, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + PT_STAGES * STAGE_BYTES);  // [PT_STAGES]
-  uint64_t *acc_full = empty_bar + PT_STAGES;                                           // [2]
-  uint64_t *acc_empty = acc_full + 2;                                                   // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *coef_a = reinterpret_cast<float *>(tiles + PT_STAGES * STAGE_BYTES + 256);     // [3][PT_KMAX]
-  float *scratch = coef_a + 3 * PT_KMAX;
-  __shared__ float red[2][4][128];  // per-epilogue-warp column partials of one tile
+  unsigned char *ring_a = tiles, *ring_b = tiles + BK_A_STAGES * BK_A_BYTES;
+  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + BK_RING);  // [2]: MMAs of k-block kb done (A stage kb%2, B stage kb%4)
+  uint64_t *full_b = empty_bar + BK_A_STAGES;                           // [4]: weight stage landed
+  uint64_t *done_bar = full_b + BK_B_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  float *coef_a = reinterpret_cast<float *>(tiles + BK_RING + 256);     // [3][TC_KMAX]
+  __shared__ float red[2][TC_THREADS / 32][32];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int ntn = (g.N + TN - 1) / TN;
-  const int ntiles = ((g.M + TM - 1) / TM) * ntn;
+  const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
+  const int m0 = m_tile * TM, n0 = n_tile * TN;
   const int num_kb = (g.K + TK - 1) / TK;
+  const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
 
   if (tid == 0) {
-    for (int s = 0; s < PT_STAGES; ++s) mbar_init(&empty_bar[s], 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int s = 0; s < BK_A_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < BK_B_STAGES; ++s) mbar_init(&full_b[s], 1);
+    mbar_init(done_bar, 1);
     mbar_fence_init();
+    fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
+    for (int kb = 0; kb < 2 && kb < num_kb; ++kb) {
+      mbar_expect_tx(&full_b[kb], BK_B_BYTES);
+      bulk_g2s(ring_b + kb * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[kb]);
+    }
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  stage_coef<AKIND>(g.A, coef_a, PT_KMAX, 0, min(g.K, PT_KMAX), tid, PT_THREADS);
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+
+  const uint32_t idesc = idesc_tf32(TM, TN, false);
+  constexpr int R = TC_ROWS_PER_THREAD;
+  const int chunk = tid & 7, rsub = tid >> 3;
+  uint32_t off[R];
+  RowCtx ca[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    off[i] = sw128_offset(rsub + 64 * i, chunk);
+    ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+  }
+  // A prefetch: DEPTH k-blocks ahead of the one being staged (register sets rr[0] = current .. rr[DEPTH])
+  constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 2 : 3;  // DYPOOL carries 9 registers per chunk: 2 sets ahead fit
+  Raw rr[DEPTH + 1][R];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+    for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
+  stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(TM, TN);
+  const uint32_t tmem_d = *tmem_slot;
 
-  if (warp < PT_PRODUCERS / 32) {
-    // ================= producers (+ MMA issue by thread 0) =================
-    const int chunk = tid & 7, rsub = tid >> 3;  // rows rsub + 32*i, i < 4
-    uint32_t off[4];
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
+    // 1. A loads of k-block kb + DEPTH in flight
 #pragma unroll
-    for (int i = 0; i < 4; ++i) off[i] = sw128_offset(rsub + 32 * i, chunk);
-    RowCtx ca[4], cb[4];
-    Raw ra[4], rb[4];
-    int t = blockIdx.x;
-    auto tile_ctx = [&](int tile, RowCtx (&xa)[4], RowCtx (&xb)[4]) {
-      const int m0 = (tile / ntn) * TM, n0 = (tile % ntn) * TN;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xa[i] = row_ctx<AKIND>(g.A, tile < ntiles ? m0 + rsub + 32 * i : 0x7fffffff);
-        xb[i] = row_ctx<PN2_ROWS_PLAIN>(g.B, tile < ntiles ? n0 + rsub + 32 * i : 0x7fffffff);
-      }
-    };
-    tile_ctx(t, ca, cb);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca[i], chunk * 4);
-      rb[i] = fetch_raw<PN2_ROWS_PLAIN>(g.B, cb[i], chunk * 4);
+    for (int i = 0; i < R; ++i)
+      rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
+    // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
+    if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
+    if (tid == 0 && kb + 2 < num_kb) {
+      const int s2 = (kb + 2) & (BK_B_STAGES - 1);
+      mbar_expect_tx(&full_b[s2], BK_B_BYTES);
+      bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
     }
-    int it = 0;  // k-blocks staged so far by this CTA (stage ring position)
-    for (int ti = 0; t < ntiles; ++ti, t += gridDim.x) {
-      const int buf = ti & 1;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % PT_STAGES;
-        // 1. next k-block's loads in flight (the next tile's first block when this is the tile's last one)
-        const bool last = kb + 1 == num_kb;
-        RowCtx na[4], nb[4];
-        Raw ra_next[4], rb_next[4];
-        if (last) tile_ctx(t + gridDim.x, na, nb);
-        const int kcol = (last ? 0 : (kb + 1) * TK) + chunk * 4;
+    // 3. transform + split + store A
+    unsigned char *st = ring_a + sa * BK_A_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ra_next[i] = fetch_raw<AKIND>(g.A, last ? na[i] : ca[i], kcol);
-          rb_next[i] = fetch_raw<PN2_ROWS_PLAIN>(g.B, last ? nb[i] : cb[i], kcol);
-        }
-        // 2. wait until the MMAs that read this stage have completed
-        if (it >= PT_STAGES) mbar_wait(&empty_bar[s], ((it / PT_STAGES) - 1) & 1);
-        unsigned char *st = tiles + s * STAGE_BYTES;
-        // 3. transform + split + store
-        const int kc = kb * TK + chunk * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 va = apply_raw<AKIND>(g.A, ca[i], kc, ra[i], coef_a, PT_KMAX, 0);
-          const float4 vb = apply_raw<PN2_ROWS_PLAIN>(g.B, cb[i], kc, rb[i], coef_a, PT_KMAX, 0);
-          float4 hi, lo;
-          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-          split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-          split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, PT_PRODUCERS);
-        if (tid == 0) {
-          if (kb == 0 && ti >= 2) mbar_wait(&acc_empty[buf], ((ti >> 1) - 1) & 1);  // epilogue drained this accumulator
-          tc_fence_after_sync();
-          const uint32_t base = smem_addr(st);
-          const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + TILE_BYTES);
-          const uint64_t b_hi = smem_desc_sw128(base + 2 * TILE_BYTES), b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-          const uint32_t d = tmem_base + buf * 128;
-#pragma unroll
-          for (int ks = 0; ks < TK / 8; ++ks) {
-            const uint64_t adv = static_cast<uint64_t>(2 * ks);
-            mma_tf32(d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-            mma_tf32(d, a_hi + adv, b_lo + adv, idesc, true);
-            mma_tf32(d, a_lo + adv, b_hi + adv, idesc, true);
-          }
-          mma_commit(&empty_bar[s]);
-          if (last) mma_commit(&acc_full[buf]);
-        }
-        // 4. rotate
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ra[i] = ra_next[i];
-          rb[i] = rb_next[i];
-          if (last) { ca[i] = na[i]; cb[i] = nb[i]; }
-        }
-      }
+    for (int i = 0; i < R; ++i) {
+      const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
+      float4 hi, lo;
+      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+      *reinterpret_cast<float4 *>(st + off[i]) = hi;
+      *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
     }
-  } else {
-    // ================= epilogue warps =================
-    const int ew = warp - PT_PRODUCERS / 32;  // 0..3 = TMEM lane quarter = 32-row block of the tile
-    const int etid = tid - PT_PRODUCERS;
-    float *wt_tile = scratch + ew * (32 * 36);
-    const int cq = lane & 7, rs = lane >> 3;
-    int ti = 0;
-    for (int t = blockIdx.x; t < ntiles; ++ti, t += gridDim.x) {
-      const int buf = ti & 1;
-      const int m0 = (t / ntn) * TM, n0 = (t % ntn) * TN;
-      const int rbase = m0 + ew * 32;
-      mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c_local = cc * 32;
-        const int col = n0 + c_local + cq * 4;
-        {
-          float v[32];
-          tmem_ld32(tmem_base + buf * 128 + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(c_local), v);
-          if (cc == 3) {  // accumulator fully read: hand it back to the MMA issuer
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
-          }
+      const uint32_t abase = smem_addr(st), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+      const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
+      const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4 *>(wt_tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        __syncwarp();
-        const bool col_ok = col < g.N;
-        float4 sc = zero4(), sh = zero4();
-        if (EPI == TC_EPI_DGRAD_MASK && col_ok) {
-          sc = ldg4(g.prev_scale + col);
-          sh = ldg4(g.prev_shift + col);
-        }
-        float4 s1 = zero4(), s2 = zero4();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = rs + 4 * i;
-          const int row = rbase + rr;
-          float4 v = *reinterpret_cast<const float4 *>(wt_tile + rr * 36 + cq * 4);
-          if (row >= g.M || !col_ok) continue;
-          if (EPI == TC_EPI_SCATTER) {
-            const int cloud = row / (g.G.npoint * g.G.nsample);
-            const size_t src = static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.G.idx + row);
-            const int fc = g.G.feat_cols;
-            if (col < fc) {
-              if (g.dfeat) {
-                float *dst = g.dfeat + src * g.ldf + col;
-                atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
-              }
-            } else if (col == fc && g.dxyz && g.G.use_xyz) {
-              const float gx = __fdiv_rn(v.x, g.G.inv_scale), gy = __fdiv_rn(v.y, g.G.inv_scale),
-                          gz = __fdiv_rn(v.z, g.G.inv_scale);
-              float *dn = g.dxyz + src * 3;
-              atomicAdd(dn + 0, gx); atomicAdd(dn + 1, gy); atomicAdd(dn + 2, gz);
-              const int centre = row / g.G.nsample;
-              float *dc = g.dxyz + (static_cast<size_t>(cloud) * g.G.n_src + __ldg(g.centre_src + centre)) * 3;
-              atomicAdd(dc + 0, -gx); atomicAdd(dc + 1, -gy); atomicAdd(dc + 2, -gz);
-            }
-            continue;
-          }
-          float4 qv;
-          if (EPI == TC_EPI_DGRAD_MASK) {
-            const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
-            v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
-            v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
-            v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
-            v.w = fmaf(y.w, sc.w, sh.w) > 0.f ? v.w : 0.f;
-            qv = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
-          } else {
-            qv = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-          }
-          *reinterpret_cast<float4 *>(g.out + static_cast<size_t>(row) * g.ldo + col) = v;
-          s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-          s2.x += qv.x; s2.y += qv.y; s2.z += qv.z; s2.w += qv.w;
-        }
-        __syncwarp();
-        if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
-          }
-          if (lane < 8) {
-            *reinterpret_cast<float4 *>(&red[0][ew][c_local + cq * 4]) = s1;
-            *reinterpret_cast<float4 *>(&red[1][ew][c_local + cq * 4]) = s2;
-          }
-        }
+      for (int ks = 0; ks < TK / 8; ++ks) {
+        const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+        mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+        mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+        mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
       }
-      if ((EPI == TC_EPI_STORE_STATS || EPI == TC_EPI_DGRAD_MASK) && g.stats != nullptr) {
-        named_bar_sync(2, PT_EPILOGUE);
-        const int c = n0 + etid;  // one column per epilogue thread
-        if (c < g.stats_ld) {
-          const float a = red[0][0][etid] + red[0][1][etid] + red[0][2][etid] + red[0][3][etid];
-          const float b = red[1][0][etid] + red[1][1][etid] + red[1][2][etid] + red[1][3][etid];
-          float *dst = g.stats + static_cast<size_t>(t / ntn) * 2 * g.stats_ld + c;
-          dst[0] = a;
-          dst[g.stats_ld] = b;
-        }
-        named_bar_sync(2, PT_EPILOGUE);
-      }
+      mma_commit(&empty_bar[sa]);
+      if (kb == num_kb - 1) mma_commit(done_bar);
     }
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+      for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
   }
+  if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
+  tc_fence_after_sync();
+
+  tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem_base);
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
 template <int AKIND, int EPI>
-int launch_tc_persistent(const GemmArgs &g, cudaStream_t stream) {
-  auto kernel = gemm_tc_persistent_kernel<AKIND, EPI>;
+int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
+  auto kernel = gemm_tc_bulk_kernel<AKIND, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
     configured_dev = dev;
   }
-  const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
-  kernel<<<grid, PT_THREADS, PT_SMEM, stream>>>(g);
-  return check_launch("gemm_tc_persistent_kernel");
+  const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
+  kernel<<<grid, TC_THREADS, BK_SMEM, stream>>>(g);
+  return check_launch("gemm_tc_bulk_kernel");
 }
 
 template <int AKIND, int BKIND, bool TRANS, int EPI>
@@ -669,18 +586,15 @@ bool gemm_tc_enabled() {
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
-  // The persistent, warp-specialised variant is correct but measured slower than one tile per 512-thread CTA
-  // (profiles/r1_gemm_bench_*): with only 8 producer warps the operand staging, not the prologue/epilogue,
-  // becomes the bottleneck.  It stays selectable for experiments: PN2_TC_PERSISTENT=1.
-  static const bool persistent = [] {
-    const char *e = getenv("PN2_TC_PERSISTENT");
-    return e != nullptr && e[0] == '1';
+  // PN2_TC_BULK=0 keeps every operand thread-staged (gemm_tc_kernel) for A/B measurements
+  static const bool bulk_on = [] {
+    const char *e = getenv("PN2_TC_BULK");
+    return e == nullptr || e[0] != '0';
   }();
-  const bool needs_coef = akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER;
-  const bool use_pt = persistent && !(needs_coef && g.K > PT_KMAX);
+  const bool use_bulk = bulk_on && g.b_img != nullptr;
 #define PN2_TC_CASE(AK, EP)                                                   \
   if (akind == AK && epi == EP)                                               \
-    return use_pt ? launch_tc_persistent<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
+    return use_bulk ? launch_tc_bulk<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)

@@ -97,6 +97,9 @@ struct GemmArgs {
   int ldf;
   float *dxyz;
   const int *centre_src;
+  // tcgen05 forward / dgrad: pre-split, pre-swizzled image of B (pn2_mlp_prep_weights), or null
+  const float *b_img;
+  int b_img_kblocks;
 };
 
 }  // namespace

@@ -153,20 +153,29 @@ def _bn_forward(L, bn, stats, tiles, rows):
     L.scale, L.shift, L.mean, L.invstd = K.bn_finalize(training, tiles, L.cout, L.np, count, stats, sums, bn)
 
 
-def _run_mlp(layers, rows0, nrows, xyz_first, feat_pad, need_grad):
-    """Forward through the conv+BN(+ReLU) stack; returns the per-layer state list."""
-    state = []
-    src, kp = rows0, rows0.cols
+def _prep_layers(layers, kp0, xyz_first, feat_pad):
+    """Per-layer geometry + prepared weights (independent of the activations, so callers issue this before they
+    wait for anything else)."""
+    state, kp = [], kp0
     for li, (conv, bn) in enumerate(layers):
         L = _Layer()
         L.cout, L.cin = conv.weight.shape[0], conv.weight.shape[1]
         L.kp, L.np = kp, pad4(L.cout)
         L.xyz_first, L.feat_pad = (xyz_first, feat_pad) if li == 0 else (0, 0)
         L.wt, L.wp = K.mlp_prep_weights(conv.weight.detach().view(L.cout, L.cin), L.xyz_first, L.feat_pad, L.kp, L.np)
+        state.append(L)
+        kp = L.np
+    return state
+
+
+def _run_mlp(layers, state, rows0, nrows):
+    """Forward through the conv+BN(+ReLU) stack; fills the per-layer state list made by _prep_layers."""
+    assert rows0.cols == state[0].kp
+    src = rows0
+    for L, (conv, bn) in zip(state, layers):
         L.y, stats, tiles = K.mlp_forward(src, L.kp, L.np, L.wt, L.wp, want_stats=bn.training)
         _bn_forward(L, bn, stats, tiles, nrows)
-        state.append(L)
-        src, kp = K.rows_bnrelu(L.y, nrows, L.np, L.np, L.scale, L.shift), L.np
+        src = K.rows_bnrelu(L.y, nrows, L.np, L.np, L.scale, L.shift)
     return state
 
 
@@ -229,6 +238,18 @@ class _SAFunction(torch.autograd.Function):
                 new_xyz = K.gather_points(xyz_c.transpose(1, 2).contiguous(), inds_).transpose(1, 2).contiguous()
             return xyz_c, inds_, new_xyz, K.ball_query(new_xyz, xyz_c, module.radius, ns)
 
+        use_xyz = bool(module.use_xyz)
+
+        def activation_independent():
+            # feature layout change + weight preparation do not need the geometry: on the MLP stream they run
+            # underneath FPS / ball query instead of after them
+            if features is not None:
+                feat_pm_ = _point_major(features, feat_cached)
+                ldf_ = feat_pm_.shape[1]
+            else:
+                feat_pm_, ldf_ = None, 0
+            return feat_pm_, ldf_, _prep_layers(layers, ldf_ + (4 if use_xyz else 0), 1 if use_xyz else 0, ldf_)
+
         if _SIDE_STREAM and (_SIDE_IN_GRAPH or not torch.cuda.is_current_stream_capturing()):
             main, side = torch.cuda.current_stream(xyz.device), _geom_stream(xyz.device)
             if not xyz_on_side or inds is not None:
@@ -239,23 +260,18 @@ class _SAFunction(torch.autograd.Function):
                 ready.record(side)
             xyz.record_stream(side)
             xyz_c.record_stream(side)
+            feat_pm, ldf, state = activation_independent()
             main.wait_event(ready)
             for t in (inds, new_xyz, idx):
                 t.record_stream(main)
         else:
             xyz_c, inds, new_xyz, idx = geometry()
-        if features is not None:
-            c_feat = features.shape[1]
-            feat_pm = _point_major(features, feat_cached)
-            ldf = feat_pm.shape[1]
-        else:
-            c_feat, feat_pm, ldf = 0, None, 0
-        use_xyz = bool(module.use_xyz)
+            feat_pm, ldf, state = activation_independent()
+        c_feat = features.shape[1] if features is not None else 0
         inv_scale = module.radius if module.normalize_xyz else 1.0
         rows0 = K.rows_gather(feat_pm, ldf, ldf, idx, xyz_c, new_xyz, n, m, ns, use_xyz, inv_scale)
         nrows = b * m * ns
-        need_grad = any(ctx.needs_input_grad)
-        state = _run_mlp(layers, rows0, nrows, 1 if use_xyz else 0, ldf, need_grad)
+        _run_mlp(layers, state, rows0, nrows)
         last = state[-1]
         out_pm, arg = K.bn_relu_pool(last.y, b * m, ns, last.cout, last.np, last.scale, last.shift)
         out = K.to_channel_major(out_pm, b, last.cout, m)
@@ -330,7 +346,7 @@ class _FPFunction(torch.autograd.Function):
             K.to_point_major(unknow_feats.detach().contiguous(), ld=ld1, out=x, col0=ld2)
         nrows = b * n
         rows0 = K.rows_plain(x, nrows, ldx, ldx)
-        state = _run_mlp(layers, rows0, nrows, 0, 0, any(ctx.needs_input_grad))
+        state = _run_mlp(layers, _prep_layers(layers, ldx, 0, 0), rows0, nrows)
         last = state[-1]
         out_pm, _ = K.bn_relu_pool(last.y, nrows, 1, last.cout, last.np, last.scale, last.shift, want_arg=False)
         out = K.to_channel_major(out_pm, b, last.cout, n)
