@@ -213,6 +213,11 @@ int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, const float *un
 int pn2_fp_interpolate_grad(int b, int n, int m, int c, const float *dout, int ldo, const int *idx,
                             const float *weight, float *dknown_pm, int ld_known, void *stream);
 
+/* Development aid: while `device_buf` (6 x `ctas` uint64, device memory) is installed, every CTA of the tensor-core
+ * GEMM kernels records [smid, t_start, t_prologue_done, t_mainloop_done, t_end, k_blocks] (globaltimer ns) for
+ * tools/gemm_trace.py.  Pass NULL to switch it off (the default). */
+int pn2_debug_gemm_trace(unsigned long long *device_buf, int ctas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,7 +343,8 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
 // CTA: 32 candidates, one per lane.  Every warp then resolves picks redundantly (identical arithmetic:
 // dist2(candidate, pick) is the same expression its owner thread evaluates in the next round), and the
 // next round applies all picks of the previous one to the register-resident points.
-// On a 40k-point room scan this makes ~9 picks per exchange (2047 rounds -> ~230).
+// On a 40k-point room scan this makes ~8 picks per exchange (2047 rounds -> ~250); on an FPS-ordered input
+// (levels 2-4) the interleaved point ownership below keeps it at ~10.
 template <int NW>
 struct alignas(16) FpsSmem4 {
   uint4 wcand[2][NW];                  // per-warp candidate {key, k, x bits, y bits}
@@ -378,7 +379,12 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
   idxs += static_cast<size_t>(batch) * m;
   if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
   const int T = cs * kFpsThreads;
-  const int g = static_cast<int>(my_cta) * kFpsThreads + tid;
+  // Point ownership: consecutive indices go to different CTAs, then to different warps, so that an input whose
+  // order is itself an FPS order (every level after the first samples the previous level's centres) spreads
+  // its next picks k, k+1, ... over all candidate slots instead of one warp.  k = g + i*T as before, so a
+  // thread's points share k mod bs and scan order inside a thread is the reference tie-break order.
+  const int g = (lane * NW + warp) * cs + static_cast<int>(my_cta);
+  const bool writer = my_cta == 0 && tid == 0;
 
   float px[PTS], py[PTS], pz[PTS], pt[PTS];
 #pragma unroll
@@ -399,7 +405,7 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
     sz[i * kFpsThreads + tid] = z;
   }
   const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
-  if (g == 0) {
+  if (writer) {
     idxs[0] = 0;
     if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
   }
@@ -413,20 +419,13 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
     }
     cluster_sync_all();
   }
+#pragma unroll
+  for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], x0, y0, z0), pt[i]);  // sample 0
 
-  // picks of the previous round, not yet applied to the resident points: lane q < npend holds pick q
-  float qx = x0, qy = y0, qz = z0;
-  int npend = 1;
   int j = 1;  // next output slot
   for (int round = 0; j < m; ++round) {
     const int p = round & 1;
-    // ---- apply the pending picks, then the thread's best / runner-up ----
-#pragma unroll 1
-    for (int q = 0; q < npend; ++q) {
-      const float xq = __shfl_sync(FULL, qx, q), yq = __shfl_sync(FULL, qy, q), zq = __shfl_sync(FULL, qz, q);
-#pragma unroll
-      for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], xq, yq, zq), pt[i]);
-    }
+    // ---- the thread's best / runner-up (every pick so far is already applied to pt[]) ----
     float best = -2.0f, second = -2.0f;
     int ib = 0;
 #pragma unroll
@@ -503,14 +502,16 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
       }
       bmax = __reduce_max_sync(FULL, lane < cs ? S.cbound[p][lane] : INT_MIN);
     }
-    // ---- resolve as many picks as the bound allows (every warp, identical result) ----
+    // ---- resolve as many picks as the bound allows (every warp, identical result).  Each accepted pick is
+    // applied to the thread's resident points right away: that work is independent of the candidate chain, so
+    // the warps of an SM overlap one another's redux / shuffle latency with it. ----
     int npick = 0;
     while (true) {
       const int src = warp_argmax_lane(cd, ck, valid, bs_log2);
       const int dbest = __shfl_sync(FULL, cd, src);
       if (npick == 0) {
         if (dbest < 0) {  // no point is a candidate: the reference yields index 0 from here on
-          if (g == 0)
+          if (writer)
             for (int t = j; t < m; ++t) {
               idxs[t] = 0;
               if (new_xyz) { new_xyz[t * 3 + 0] = x0; new_xyz[t * 3 + 1] = y0; new_xyz[t * 3 + 2] = z0; }
@@ -523,17 +524,17 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
       }
       const int kq = __shfl_sync(FULL, ck, src);
       const float xq = __shfl_sync(FULL, cx, src), yq = __shfl_sync(FULL, cy, src), zq = __shfl_sync(FULL, cz, src);
-      if (g == 0) {
+      if (writer) {
         idxs[j + npick] = kq;
         if (new_xyz) { new_xyz[(j + npick) * 3 + 0] = xq; new_xyz[(j + npick) * 3 + 1] = yq; new_xyz[(j + npick) * 3 + 2] = zq; }
       }
-      if (lane == npick) { qx = xq; qy = yq; qz = zq; }
       ++npick;
-      if (j + npick >= m || npick == 32) break;
       if (valid && cd >= 0) cd = __float_as_int(fminf(dist2(cx, cy, cz, xq, yq, zq), __int_as_float(cd)));
+#pragma unroll
+      for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], xq, yq, zq), pt[i]);
+      if (j + npick >= m) break;
     }
     j += npick;
-    npend = npick < 32 ? npick : 32;
   }
   if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
 }

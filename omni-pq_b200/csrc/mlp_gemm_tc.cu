@@ -102,6 +102,21 @@ __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int c
   }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+// phase stamp of CTA `cta` (thread 0 only; no-op unless a trace buffer is installed)
+__device__ __forceinline__ void trace_stamp(const GemmArgs &g, int cta, int slot, unsigned long long v) {
+  if (g.trace != nullptr && threadIdx.x == 0 && cta < g.trace_cap) g.trace[static_cast<size_t>(cta) * 6 + slot] = v;
+}
+
 // ---- epilogue (shared by the kernels below) ------------------------------------------------------------------
 // Drains the 128 x 128 fp32 accumulator at `tmem_d` of the tile at (m0, n0); `scratch` = the (now idle) operand
 // stages, `red` = per-warp column partials.  m_tile indexes the per-row-tile statistics, split the wgrad slice.
@@ -231,6 +246,9 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  trace_stamp(g, cta_id, 0, smid());
+  trace_stamp(g, cta_id, 1, globaltimer_ns());
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) mbar_init(&empty_bar[s], 1);
@@ -308,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  trace_stamp(g, cta_id, 2, globaltimer_ns());
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES;
@@ -374,12 +393,15 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   }
   if (num_kb > 0) mbar_wait(done_bar, 0);
   tc_fence_after_sync();
+  trace_stamp(g, cta_id, 3, globaltimer_ns());
 
   tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
+  trace_stamp(g, cta_id, 4, globaltimer_ns());
+  trace_stamp(g, cta_id, 5, static_cast<unsigned long long>(num_kb));
 }
 
 // ---- forward / data-gradient kernel with a bulk-copied weight operand ---------------------------------------
@@ -446,6 +468,8 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   const int m0 = m_tile * TM, n0 = n_tile * TN;
   const int num_kb = (g.K + TK - 1) / TK;
   const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
+  trace_stamp(g, blockIdx.x, 0, smid());
+  trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
 
   if (tid == 0) {
     for (int s = 0; s < BK_A_STAGES; ++s) mbar_init(&empty_bar[s], 1);
@@ -482,6 +506,7 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
   for (int kb = 0; kb < num_kb; ++kb) {
     const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
@@ -532,12 +557,15 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   }
   if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
   tc_fence_after_sync();
+  trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
 
   tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
+  trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
+  trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
 }
 
 template <int AKIND, int EPI>
@@ -551,7 +579,9 @@ int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
     configured_dev = dev;
   }
   const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
-  kernel<<<grid, TC_THREADS, BK_SMEM, stream>>>(g);
+  GemmArgs a = g;
+  gemm_trace_target(&a.trace, &a.trace_cap);
+  kernel<<<grid, TC_THREADS, BK_SMEM, stream>>>(a);
   return check_launch("gemm_tc_bulk_kernel");
 }
 
@@ -566,11 +596,21 @@ int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
     configured_dev = dev;
   }
   dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, splits);
-  kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(g);
+  GemmArgs a = g;
+  gemm_trace_target(&a.trace, &a.trace_cap);
+  kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a);
   return check_launch("gemm_tc_kernel");
 }
 
 }  // namespace
+
+// development aid: per-CTA phase timestamps of the next tensor-core GEMM launches (tools/gemm_trace.py)
+static unsigned long long *g_trace_buf = nullptr;
+static int g_trace_cap = 0;
+void gemm_trace_target(unsigned long long **buf, int *cap) {
+  *buf = g_trace_buf;
+  *cap = g_trace_cap;
+}
 
 bool gemm_tc_enabled() {
   static int on = -1;
@@ -626,3 +666,9 @@ int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream)
 }
 
 }  // namespace pn2
+
+PN2_EXPORT int pn2_debug_gemm_trace(unsigned long long *device_buf, int ctas) {
+  pn2::g_trace_buf = device_buf;
+  pn2::g_trace_cap = device_buf ? ctas : 0;
+  return PN2_OK;
+}

@@ -100,6 +100,9 @@ struct GemmArgs {
   // tcgen05 forward / dgrad: pre-split, pre-swizzled image of B (pn2_mlp_prep_weights), or null
   const float *b_img;
   int b_img_kblocks;
+  // development aid (pn2_debug_gemm_trace): per-CTA phase timestamps [smid, start, prologue, main loop, end, k-blocks]
+  unsigned long long *trace;
+  int trace_cap;
 };
 
 }  // namespace
@@ -109,5 +112,6 @@ constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
+void gemm_trace_target(unsigned long long **buf, int *cap);
 
 }  // namespace pn2

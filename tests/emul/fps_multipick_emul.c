@@ -54,9 +54,17 @@ int fps_multipick_emul(int n, int m, int cs, int bs, const float *xyz, int *idx)
     }
   const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
   idx[0] = 0;
-  float qx[32], qy[32], qz[32];
-  qx[0] = x0; qy[0] = y0; qz[0] = z0;
-  int npend = 1, j = 1, rounds = 0;
+  int j = 1, rounds = 0;
+#define APPLY_PICK(XQ, YQ, ZQ)                                                                          \
+  for (int g_ = 0; g_ < T; ++g_)                                                                        \
+    for (int i_ = 0; i_ < PTS; ++i_) {                                                                  \
+      const int k_ = g_ + i_ * T;                                                                       \
+      const float px_ = k_ < n ? xyz[k_ * 3] : 0.f, py_ = k_ < n ? xyz[k_ * 3 + 1] : 0.f,              \
+                  pz_ = k_ < n ? xyz[k_ * 3 + 2] : 0.f;                                                 \
+      float *q_ = pt + (size_t)g_ * PTS + i_;                                                           \
+      *q_ = fminf(dist2(px_, py_, pz_, (XQ), (YQ), (ZQ)), *q_);                                         \
+    }
+  APPLY_PICK(x0, y0, z0) /* sample 0 */
   Cand wc[MAXCS][NW];
   int wb[MAXCS][NW];
   while (j < m) {
@@ -65,14 +73,8 @@ int fps_multipick_emul(int n, int m, int cs, int bs, const float *xyz, int *idx)
       for (int w = 0; w < NW; ++w) {
         int kb[32], ks[32], km[32], act[32];
         for (int l = 0; l < 32; ++l) {
-          const int g = cta * THREADS + w * 32 + l;
+          const int g = (l * NW + w) * cs + cta; /* interleaved ownership, as in the kernel */
           float *p = pt + (size_t)g * PTS;
-          for (int q = 0; q < npend; ++q)
-            for (int i = 0; i < PTS; ++i) {
-              const int k = g + i * T;
-              const float px = k < n ? xyz[k * 3] : 0.f, py = k < n ? xyz[k * 3 + 1] : 0.f, pz = k < n ? xyz[k * 3 + 2] : 0.f;
-              p[i] = fminf(dist2(px, py, pz, qx[q], qy[q], qz[q]), p[i]);
-            }
           float best = -2.0f, second = -2.0f;
           int ib = 0;
           for (int i = 0; i < PTS; ++i) {
@@ -124,14 +126,13 @@ int fps_multipick_emul(int n, int m, int cs, int bs, const float *xyz, int *idx)
       } else if (dbest <= bmax) break;
       const float xq = c[src].x, yq = c[src].y, zq = c[src].z;
       idx[j + npick] = ck[src];
-      qx[npick] = xq; qy[npick] = yq; qz[npick] = zq;
       ++npick;
-      if (j + npick >= m || npick == 32) break;
       for (int l = 0; l < 32; ++l)
         if (valid[l] && cd[l] >= 0) cd[l] = fkey(fminf(dist2(c[l].x, c[l].y, c[l].z, xq, yq, zq), keyf(cd[l])));
+      APPLY_PICK(xq, yq, zq) /* the kernel applies an accepted pick to the resident points at once */
+      if (j + npick >= m) break;
     }
     j += npick;
-    npend = npick < 32 ? npick : 32;
   }
   free(pt);
   return rounds;
