@@ -27,7 +27,8 @@ namespace {
 using namespace sm100;
 
 constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
-constexpr int TC_THREADS = 512;                    // 16 warps: latency hiding for the producers / epilogue
+constexpr int TC_THREADS = 512;                    // 16 producer / epilogue warps
+constexpr int TC_CTA_THREADS = TC_THREADS + 32;    // + one warp whose lane 0 only issues the MMAs
 constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
@@ -117,13 +118,62 @@ __device__ __forceinline__ void trace_stamp(const GemmArgs &g, int cta, int slot
   if (g.trace != nullptr && threadIdx.x == 0 && cta < g.trace_cap) g.trace[static_cast<size_t>(cta) * 6 + slot] = v;
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// mbarrier wait that traps instead of hanging the GPU if a transaction count was ever wrong
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && (spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// barrier over the 512 producer / epilogue threads only (the MMA warp does not take part)
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 // ---- epilogue (shared by the kernels below) ------------------------------------------------------------------
 // Drains the 128 x 128 fp32 accumulator at `tmem_d` of the tile at (m0, n0); `scratch` = the (now idle) operand
 // stages, `red` = per-warp column partials.  m_tile indexes the per-row-tile statistics, split the wgrad slice.
+// DGRAD_MASK reads the previous layer's pre-activations next to every output element: issue those loads before
+// the accumulator is complete, so their latency hides behind the tail of the MMAs and the TMEM drain.
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_prefetch(const GemmArgs &g, int m0, int n0, float4 (&yv)[8]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = n0 + (warp >> 2) * 32 + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (warp & 3) * 32 + (lane >> 3) + 4 * i;
+    yv[i] = zero4();
+    if (EPI == TC_EPI_DGRAD_MASK && row < g.M && col < g.N) yv[i] = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, unsigned char *tiles,
                                             float (&red)[2][TC_THREADS / 32][32], int m0, int n0, int m_tile, int split,
-                                            bool have_acc) {
+                                            bool have_acc, const float4 (&yv)[8]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 16 warps, one 32 x 32 chunk each: warp w reads TMEM lanes 32*(w%4)..+31 (tile rows), columns 32*(w/4)..+31.
   // The chunk goes through a per-warp shared-memory tile (row stride 36 floats, conflict-free 128-bit accesses
@@ -181,7 +231,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
     }
     float4 qv;
     if (EPI == TC_EPI_DGRAD_MASK) {
-      const float4 y = ldg4(g.prev_y + static_cast<size_t>(row) * g.ld_prev + col);
+      const float4 y = yv[i];
       v.x = fmaf(y.x, sc.x, sh.x) > 0.f ? v.x : 0.f;
       v.y = fmaf(y.y, sc.y, sh.y) > 0.f ? v.y : 0.f;
       v.z = fmaf(y.z, sc.z, sh.z) > 0.f ? v.z : 0.f;
@@ -207,7 +257,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
       *reinterpret_cast<float4 *>(&red[0][warp][cq * 4]) = s1;
       *reinterpret_cast<float4 *>(&red[1][warp][cq * 4]) = s2;
     }
-    __syncthreads();
+    producers_sync();
     if (tid < 128) {  // tid -> (column group h = tid/32: warps 4h..4h+3 hold its four row blocks, column l)
       const int h = tid >> 5, l = tid & 31;
       const int c = n0 + h * 32 + l;
@@ -233,12 +283,13 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
 // Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
 // 128-bit access touches 4 lines instead of 32.
 template <int AKIND, int BKIND, bool TRANS, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + TC_STAGES * STAGE_BYTES);  // [TC_STAGES]
-  uint64_t *done_bar = empty_bar + TC_STAGES;
+  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + TC_STAGES * STAGE_BYTES);  // [TC_STAGES] MMAs of the stage done
+  uint64_t *full_bar = empty_bar + TC_STAGES;                                           // [TC_STAGES] stage written (16 warps)
+  uint64_t *done_bar = full_bar + TC_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
   float *coef_a = reinterpret_cast<float *>(tiles + TC_STAGES * STAGE_BYTES + 256);  // [3][coef_ld_a]
   float *coef_b = coef_a + 3 * TC_KMAX;                                              // [2][128]
@@ -251,11 +302,15 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, cta_id, 1, globaltimer_ns());
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], TC_THREADS / 32);
+    }
     mbar_init(done_bar, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs, nothing else
 
   const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
@@ -296,106 +351,121 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   };
   RowCtx na[R], nb[R];  // transposed form: contexts of the NEXT k-block, resolved one block ahead of its loads so
                         // that a gather's index load and the row loads that depend on it sit in different iterations
-  if (TRANS) {
-    make_ctx(0, ca, cb);
-    make_ctx(1, na, nb);
-  } else {
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
-      cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 64 * i);
-    }
-  }
   auto col_a = [&](int kb) { return TRANS ? m0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
   auto col_b = [&](int kb) { return TRANS ? n0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
-
   Raw ra[R], rb[R], ra_next[R], rb_next[R];
-  if (num_kb > 0) {
+  if (producer) {
+    if (TRANS) {
+      make_ctx(0, ca, cb);
+      make_ctx(1, na, nb);
+    } else {
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
-      rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
+      for (int i = 0; i < R; ++i) {
+        ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+        cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 64 * i);
+      }
     }
+    if (num_kb > 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
+        rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
+      }
+    }
+    // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
+    // tile's 128 output rows / columns for the transposed form); staged while the first k-block's loads fly
+    stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
+    if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
   }
-
-  // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
-  // tile's 128 output rows / columns for the transposed form); staged while the first k-block's loads fly
-  stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
-  if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, cta_id, 2, globaltimer_ns());
 
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const int s = kb % TC_STAGES;
-    // 1. put the next k-block's loads in flight, then resolve the contexts of the block after it
-    if (kb + 1 < num_kb) {
+  if (!producer) {
+    // ---- MMA warp: one thread waits for each stage to be written, issues its 12 MMAs and commits them to the
+    // stage's "empty" barrier.  It is NOT a producer: a thread that stages operands and then issues MMAs keeps
+    // its whole warp (and, through the block barrier, every producer) waiting while the tensor-pipe queue
+    // accepts them -- measured 1.3-1.9 us per k-block against 0.42 us of MMA time (profiles/c3_gemm_trace.txt).
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
+        uint64_t a_hi, a_lo, b_hi, b_lo, step;
+        if (TRANS) {
+          a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
+          b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
+          b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
+          step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
+        } else {
+          a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+          b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+          step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
+        }
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t adv = step * ks;
+          mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+          mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+          mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+        }
+        mma_commit(&empty_bar[s]);
+        if (kb == num_kb - 1) mma_commit(done_bar);
+      }
+    }
+  } else {
+    // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
+    // per warp and reclaimed when the MMAs that read it have completed
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % TC_STAGES;
+      // 1. put the next k-block's loads in flight, then resolve the contexts of the block after it
+      if (kb + 1 < num_kb) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
+          rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
+        }
+      }
+      // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
+      if (kb >= TC_STAGES) mbar_wait_guarded(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
+      unsigned char *st = tiles + s * STAGE_BYTES;
+      // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
-        rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
+        const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
+        const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
+        float4 hi, lo;
+        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
+        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
+        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
+        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
       }
-    }
-    // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
-    if (kb >= TC_STAGES) mbar_wait(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
-    unsigned char *st = tiles + s * STAGE_BYTES;
-    // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
+      fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      // 4. rotate the prefetch registers
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
-      const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
-      float4 hi, lo;
-      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-      *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-      split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-      split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-      *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-      const uint32_t base = smem_addr(st);
-      uint64_t a_hi, a_lo, b_hi, b_lo, step;
-      if (TRANS) {
-        a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
-        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
-        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
-        step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
-      } else {
-        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
-        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
+      for (int i = 0; i < R; ++i) {
+        ra[i] = ra_next[i];
+        rb[i] = rb_next[i];
+        if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
       }
-#pragma unroll
-      for (int ks = 0; ks < TK / 8; ++ks) {
-        const uint64_t adv = step * ks;
-        mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-        mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-        mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
-      }
-      mma_commit(&empty_bar[s]);
-      if (kb == num_kb - 1) mma_commit(done_bar);
+      if (TRANS) make_ctx(kb + 2, na, nb);
     }
-    // 4. rotate the prefetch registers
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      ra[i] = ra_next[i];
-      rb[i] = rb_next[i];
-      if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
-    }
-    if (TRANS) make_ctx(kb + 2, na, nb);
+    float4 yv[8];
+    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
+    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
+    tc_fence_after_sync();
+    trace_stamp(g, cta_id, 3, globaltimer_ns());
+    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0, yv);
   }
-  if (num_kb > 0) mbar_wait(done_bar, 0);
-  tc_fence_after_sync();
-  trace_stamp(g, cta_id, 3, globaltimer_ns());
-
-  tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
@@ -420,49 +490,22 @@ constexpr int BK_A_BYTES = 2 * TILE_BYTES, BK_B_BYTES = 2 * TILE_BYTES;  // hi +
 constexpr int BK_RING = BK_A_STAGES * BK_A_BYTES + BK_B_STAGES * BK_B_BYTES;
 constexpr int BK_SMEM = BK_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-// mbarrier wait that traps instead of hanging the GPU if a transaction count was ever wrong
-__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
-  const uint32_t a = smem_addr(bar);
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (!done && (spins & 1023u) == 1023u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
-    }
-  }
-}
-
 template <int AKIND, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char *ring_a = tiles, *ring_b = tiles + BK_A_STAGES * BK_A_BYTES;
   uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + BK_RING);  // [2]: MMAs of k-block kb done (A stage kb%2, B stage kb%4)
-  uint64_t *full_b = empty_bar + BK_A_STAGES;                           // [4]: weight stage landed
+  uint64_t *full_a = empty_bar + BK_A_STAGES;                           // [2]: A stage written (one arrival per producer warp)
+  uint64_t *full_b = full_a + BK_A_STAGES;                              // [4]: weight stage landed
   uint64_t *done_bar = full_b + BK_B_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
   float *coef_a = reinterpret_cast<float *>(tiles + BK_RING + 256);     // [3][TC_KMAX]
   __shared__ float red[2][TC_THREADS / 32][32];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs (see gemm_tc_kernel)
   const int ntn = (g.N + TN - 1) / TN;
   const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
   const int m0 = m_tile * TM, n0 = n_tile * TN;
@@ -472,7 +515,10 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
 
   if (tid == 0) {
-    for (int s = 0; s < BK_A_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < BK_A_STAGES; ++s) {
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_a[s], TC_THREADS / 32);
+    }
     for (int s = 0; s < BK_B_STAGES; ++s) mbar_init(&full_b[s], 1);
     mbar_init(done_bar, 1);
     mbar_fence_init();
@@ -489,77 +535,88 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   const int chunk = tid & 7, rsub = tid >> 3;
   uint32_t off[R];
   RowCtx ca[R];
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    off[i] = sw128_offset(rsub + 64 * i, chunk);
-    ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
-  }
   // A prefetch: DEPTH k-blocks ahead of the one being staged (register sets rr[0] = current .. rr[DEPTH])
   constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 2 : 3;  // DYPOOL carries 9 registers per chunk: 2 sets ahead fit
   Raw rr[DEPTH + 1][R];
+  if (producer) {
 #pragma unroll
-  for (int d = 0; d < DEPTH; ++d)
+    for (int i = 0; i < R; ++i) {
+      off[i] = sw128_offset(rsub + 64 * i, chunk);
+      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+    }
 #pragma unroll
-    for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
-  stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
+    for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+      for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
+    stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
-    // 1. A loads of k-block kb + DEPTH in flight
+  if (!producer) {
+    if (lane == 0) {  // ---- MMA thread
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
+        mbar_wait_guarded(&full_a[sa], (kb >> 1) & 1);
+        mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
+        tc_fence_after_sync();
+        const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+        const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
+        const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-      rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
-    // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
-    if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
-    if (tid == 0 && kb + 2 < num_kb) {
-      const int s2 = (kb + 2) & (BK_B_STAGES - 1);
-      mbar_expect_tx(&full_b[s2], BK_B_BYTES);
-      bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
-    }
-    // 3. transform + split + store A
-    unsigned char *st = ring_a + sa * BK_A_BYTES;
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
-      float4 hi, lo;
-      split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-      split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-      *reinterpret_cast<float4 *>(st + off[i]) = hi;
-      *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
-      tc_fence_after_sync();
-      const uint32_t abase = smem_addr(st), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-      const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
-      const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
-#pragma unroll
-      for (int ks = 0; ks < TK / 8; ++ks) {
-        const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-        mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-        mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-        mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+          mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+          mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+          mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+        }
+        mma_commit(&empty_bar[sa]);
+        if (kb == num_kb - 1) mma_commit(done_bar);
       }
-      mma_commit(&empty_bar[sa]);
-      if (kb == num_kb - 1) mma_commit(done_bar);
     }
+  } else {
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sa = kb & (BK_A_STAGES - 1);
+      // 1. A loads of k-block kb + DEPTH in flight
 #pragma unroll
-    for (int d = 0; d < DEPTH; ++d)
+      for (int i = 0; i < R; ++i)
+        rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
+      // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
+      if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
+      if (tid == 0 && kb + 2 < num_kb) {
+        const int s2 = (kb + 2) & (BK_B_STAGES - 1);
+        mbar_expect_tx(&full_b[s2], BK_B_BYTES);
+        bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
+      }
+      // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
+      unsigned char *st = ring_a + sa * BK_A_BYTES;
 #pragma unroll
-      for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
+      for (int i = 0; i < R; ++i) {
+        const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
+        float4 hi, lo;
+        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(st + off[i]) = hi;
+        *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[sa]);
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
+    }
+    float4 yv[8];
+    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
+    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
+    tc_fence_after_sync();
+    trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
+    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
   }
-  if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
-  tc_fence_after_sync();
-  trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
-
-  tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0);
 
   tc_fence_before_sync();
   __syncthreads();
@@ -581,7 +638,7 @@ int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
-  kernel<<<grid, TC_THREADS, BK_SMEM, stream>>>(a);
+  kernel<<<grid, TC_CTA_THREADS, BK_SMEM, stream>>>(a);
   return check_launch("gemm_tc_bulk_kernel");
 }
 
@@ -598,7 +655,7 @@ int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
   dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, splits);
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
-  kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a);
+  kernel<<<grid, TC_CTA_THREADS, TC_SMEM, stream>>>(a);
   return check_launch("gemm_tc_kernel");
 }
 
