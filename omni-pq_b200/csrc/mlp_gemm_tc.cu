@@ -566,12 +566,14 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
         const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
         const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
         const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+        if (g.debug != 1 || kb == 0) {
 #pragma unroll
-        for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-          mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-          mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-          mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+          for (int ks = 0; ks < TK / 8; ++ks) {
+            const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+          }
         }
         mma_commit(&empty_bar[sa]);
         if (kb == num_kb - 1) mma_commit(done_bar);
@@ -593,14 +595,16 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
       }
       // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
       unsigned char *st = ring_a + sa * BK_A_BYTES;
+      if (g.debug != 2) {
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
-        float4 hi, lo;
-        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + off[i]) = hi;
-        *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+        for (int i = 0; i < R; ++i) {
+          const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
+          float4 hi, lo;
+          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -638,6 +642,11 @@ int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
+  static const int debug = [] {
+    const char *e = getenv("PN2_TC_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  a.debug = debug;
   kernel<<<grid, TC_CTA_THREADS, BK_SMEM, stream>>>(a);
   return check_launch("gemm_tc_bulk_kernel");
 }
