@@ -629,6 +629,177 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
 }
 
+// ---- forward / data-gradient kernel with the A operand in tensor memory -------------------------------------
+// Measured on gemm_tc_bulk_kernel (profiles/c5_gemm_floor.txt): a k-block costs ~1.0 us against 0.40 us of MMA
+// time, and the same loop with the MMAs removed still needs 0.7 us -- the producer -> MMA-thread -> producer
+// hand-over of a shared-memory A stage (proxy fence, barrier round trip) is ~1.4 us long and a 2-stage ring
+// hides only half of it; the 192 KB of shared memory are full, so the ring cannot get deeper there.  The A
+// operand is produced in REGISTERS anyway (row source + hi/lo split), so this kernel writes it straight into
+// tensor memory with tcgen05.st (thread = tile row = TMEM lane, 8 consecutive k columns per warp quarter) and
+// the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc): no shared-memory traffic and no proxy fence for
+// A, 6 A stages in the 384 TMEM columns next to the accumulator, and all of shared memory for a 6-stage ring
+// of the bulk-copied weight image.  Shared-memory traffic per k-block drops from 160 KB to 80 KB.
+// Warps 0-15: producers + epilogue, warp 16: MMA issue (lane 0), warp 17: weight-stage loader (lane 0).
+constexpr int TS_A_STAGES = 6, TS_B_STAGES = 6;
+constexpr int TS_THREADS = TC_THREADS + 64;
+constexpr uint32_t TS_TMEM_COLS = 512, TS_A_COL0 = 128, TS_A_STAGE_COLS = 64;  // per stage: 32 hi + 32 lo columns
+constexpr int TS_RING = TS_B_STAGES * BK_B_BYTES;
+constexpr int TS_SMEM = TS_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
+
+template <int AKIND, int EPI>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gemm_tc_ts_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char *ring_b = tiles;
+  uint64_t *empty_a = reinterpret_cast<uint64_t *>(tiles + TS_RING);  // [6] MMAs that read A stage s have completed
+  uint64_t *full_a = empty_a + TS_A_STAGES;                           // [6] A stage written (one arrival per producer warp)
+  uint64_t *empty_b = full_a + TS_A_STAGES;                           // [6] MMAs that read weight stage s have completed
+  uint64_t *full_b = empty_b + TS_B_STAGES;                           // [6] weight stage landed
+  uint64_t *done_bar = full_b + TS_B_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  float *coef_a = reinterpret_cast<float *>(tiles + TS_RING + 256);   // [3][TC_KMAX]
+  __shared__ float red[2][TC_THREADS / 32][32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp < TC_THREADS / 32;
+  const int ntn = (g.N + TN - 1) / TN;
+  const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
+  const int m0 = m_tile * TM, n0 = n_tile * TN;
+  const int num_kb = (g.K + TK - 1) / TK;
+  const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
+  trace_stamp(g, blockIdx.x, 0, smid());
+  trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
+
+  if (tid == 0) {
+    for (int s = 0; s < TS_A_STAGES; ++s) {
+      mbar_init(&empty_a[s], 1);
+      mbar_init(&full_a[s], TC_THREADS / 32);
+    }
+    for (int s = 0; s < TS_B_STAGES; ++s) {
+      mbar_init(&empty_b[s], 1);
+      mbar_init(&full_b[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
+  }
+  if (warp == 0) tmem_alloc<TS_TMEM_COLS>(tmem_slot);
+
+  const uint32_t idesc = idesc_tf32(TM, TN, false);
+  // producer mapping: thread = tile row 32*(warp%4) + lane (its TMEM lane), columns 8*(warp/4)..+7 of the k-block
+  constexpr int R = 2;
+  const int quarter = warp & 3, cgrp = (warp >> 2) & 3;
+  RowCtx ca;
+  constexpr int DEPTH = (AKIND == PN2_ROWS_DYPOOL || AKIND == PN2_ROWS_DY) ? 2 : 3;  // register budget: 96 per thread
+  Raw rr[DEPTH + 1][R];
+  auto col_of = [&](int kb, int j) { return kb < num_kb ? kb * TK + cgrp * 8 + 4 * j : 0x3fffffff; };
+  if (producer) {
+    ca = row_ctx<AKIND>(g.A, m0 + quarter * 32 + lane);
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+      for (int j = 0; j < R; ++j) rr[d][j] = fetch_raw<AKIND>(g.A, ca, col_of(d, j));
+    stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
+
+  if (warp == TC_THREADS / 32 + 1) {
+    if (lane == 0) {  // ---- weight loader: one 32 KB bulk copy per k-block, up to 6 in flight
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TS_B_STAGES;
+        if (kb >= TS_B_STAGES) mbar_wait_guarded(&empty_b[s], ((kb / TS_B_STAGES) - 1) & 1);
+        mbar_expect_tx(&full_b[s], BK_B_BYTES);
+        bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
+      }
+    }
+  } else if (warp == TC_THREADS / 32) {
+    if (lane == 0) {  // ---- MMA thread
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % TS_A_STAGES, sb = kb % TS_B_STAGES;
+        mbar_wait_guarded(&full_a[sa], (kb / TS_A_STAGES) & 1);
+        mbar_wait_guarded(&full_b[sb], (kb / TS_B_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_hi = tmem_d + TS_A_COL0 + sa * TS_A_STAGE_COLS, a_lo = a_hi + 32;
+        const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+        const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+          mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
+          mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, idesc, true);
+          mma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, idesc, true);
+        }
+        mma_commit(&empty_a[sa]);
+        mma_commit(&empty_b[sb]);
+        if (kb == num_kb - 1) mma_commit(done_bar);
+      }
+    }
+  } else {
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + TS_A_COL0 + cgrp * 8;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sa = kb % TS_A_STAGES;
+#pragma unroll
+      for (int j = 0; j < R; ++j) rr[DEPTH][j] = fetch_raw<AKIND>(g.A, ca, col_of(kb + DEPTH, j));
+      if (kb >= TS_A_STAGES) {
+        mbar_wait_guarded(&empty_a[sa], ((kb / TS_A_STAGES) - 1) & 1);
+        tc_fence_after_sync();
+      }
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const float4 v = apply_raw<AKIND>(g.A, ca, kb * TK + cgrp * 8 + 4 * j, rr[0][j], coef_a, TC_KMAX, 0);
+        split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+        split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+      }
+      const uint32_t dst = lane_base + sa * TS_A_STAGE_COLS;
+      tmem_st8(dst, hi);
+      tmem_st8(dst + 32, lo);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[sa]);
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int j = 0; j < R; ++j) rr[d][j] = rr[d + 1][j];
+    }
+    float4 yv[8];
+    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
+    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
+    tc_fence_after_sync();
+    trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
+    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TS_TMEM_COLS>(tmem_d);
+  trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
+  trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
+}
+
+template <int AKIND, int EPI>
+int launch_tc_ts(const GemmArgs &g, cudaStream_t stream) {
+  auto kernel = gemm_tc_ts_kernel<AKIND, EPI>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+    configured_dev = dev;
+  }
+  const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
+  GemmArgs a = g;
+  gemm_trace_target(&a.trace, &a.trace_cap);
+  kernel<<<grid, TS_THREADS, TS_SMEM, stream>>>(a);
+  return check_launch("gemm_tc_ts_kernel");
+}
+
 template <int AKIND, int EPI>
 int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
   auto kernel = gemm_tc_bulk_kernel<AKIND, EPI>;
@@ -698,9 +869,15 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     return e == nullptr || e[0] != '0';
   }();
   const bool use_bulk = bulk_on && g.b_img != nullptr;
-#define PN2_TC_CASE(AK, EP)                                                   \
-  if (akind == AK && epi == EP)                                               \
-    return use_bulk ? launch_tc_bulk<AK, EP>(g, stream) : launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream);
+  // PN2_TC_TS=0 keeps the A operand in shared memory (gemm_tc_bulk_kernel)
+  static const bool ts_on = [] {
+    const char *e = getenv("PN2_TC_TS");
+    return e == nullptr || e[0] != '0';
+  }();
+#define PN2_TC_CASE(AK, EP)                                                                     \
+  if (akind == AK && epi == EP)                                                                 \
+    return !use_bulk ? launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream)                   \
+                     : ts_on ? launch_tc_ts<AK, EP>(g, stream) : launch_tc_bulk<AK, EP>(g, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)
