@@ -345,21 +345,14 @@ fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__
 // next round applies all picks of the previous one to the register-resident points.
 // On a 40k-point room scan this makes ~8 picks per exchange (2047 rounds -> ~250); on an FPS-ordered input
 // (levels 2-4) the interleaved point ownership below keeps it at ~10.
-constexpr int kFpsOwnerWarps = kFpsThreads / 32;      // 16 warps own the points
-constexpr int kFpsCtaThreads = kFpsThreads + 32;      // + 1 resolver warp
-constexpr int kFpsMaxPicks = 64;                      // picks published per round (list size)
-constexpr unsigned kPubDone = 0x80000000u, kPubAllSkipped = 0x40000000u;
-
 template <int NW>
 struct alignas(16) FpsSmem4 {
   uint4 wcand[2][NW];                  // per-warp candidate {key, k, x bits, y bits}
   uint4 ccand[2][2 * kFpsMaxCluster];  // [c]: best of CTA c, [16 + c]: its runner-up
-  float4 pick[2][kFpsMaxPicks];        // picks of the round in order (x, y, z, -)
   float wz[2][NW];
   int wbound[2][NW];                   // best key among the warp's points other than its candidate
   float cz[2][2 * kFpsMaxCluster];
   int cbound[2][kFpsMaxCluster];       // bound over the CTA's points other than its two candidates
-  unsigned pub[2];                     // picks published so far in the round | kPubDone | kPubAllSkipped
   unsigned long long bar[2];
 };
 constexpr uint32_t kCand2Bytes = 44;   // best: v4 + z + bound, runner-up: v4 + z
@@ -367,26 +360,11 @@ constexpr uint32_t kCand2Bytes = 44;   // best: v4 + z + bound, runner-up: v4 + 
 // order-preserving int key of a min-distance: >= 0 -> float bits, "never a candidate" (-1) -> -1
 __device__ __forceinline__ int fps_key(float v) { return v < 0.f ? -1 : __float_as_int(v); }
 
-__device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_shared(unsigned *p, unsigned v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-
-// Roles: warps 0-15 own the points (registers) and apply picks; warp 16 is the RESOLVER: it alone gathers the
-// round's candidates (cluster exchange included), runs the dependent pick chain (redux -> ballot -> shuffle ->
-// distance) and publishes every accepted pick through shared memory (pick list + release store of the count),
-// which the owner warps poll and apply while the resolver is already working on the next pick.  With every
-// warp resolving redundantly (first version) the 16 copies of the chain shared one redux/shuffle pipe and a
-// pick cost ~650 cycles; the update (35 instructions per thread and pick) now overlaps the chain instead.
 template <int PTS>
-__global__ void __launch_bounds__(kFpsCtaThreads, 1)
+__global__ void __launch_bounds__(kFpsThreads, 1)
 fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                      int *__restrict__ idxs, float *__restrict__ new_xyz) {
-  constexpr int NW = kFpsOwnerWarps;
+  constexpr int NW = kFpsThreads / 32;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FpsSmem4<NW> &S = *reinterpret_cast<FpsSmem4<NW> *>(smem_raw);
@@ -395,7 +373,6 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
   float *sz = sy + PTS * kFpsThreads;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool owner = warp < NW;
   const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
   const int batch = blockIdx.x / cs;
   xyz += static_cast<size_t>(batch) * n * 3;
@@ -407,61 +384,60 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
   // its next picks k, k+1, ... over all candidate slots instead of one warp.  k = g + i*T as before, so a
   // thread's points share k mod bs and scan order inside a thread is the reference tie-break order.
   const int g = (lane * NW + warp) * cs + static_cast<int>(my_cta);
+  const bool writer = my_cta == 0 && tid == 0;
 
-  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
   float px[PTS], py[PTS], pz[PTS], pt[PTS];
-  if (owner) {
 #pragma unroll
-    for (int i = 0; i < PTS; ++i) {
-      const int k = g + i * T;
-      float x = 0.f, y = 0.f, z = 0.f;
-      bool valid = false;
-      if (k < n) {
-        x = xyz[k * 3 + 0];
-        y = xyz[k * 3 + 1];
-        z = xyz[k * 3 + 2];
-        valid = !(static_cast<double>(sq3(x, y, z)) <= 1e-3);  // sampling_gpu.cu:105-106
-      }
-      px[i] = x; py[i] = y; pz[i] = z;
-      pt[i] = valid ? 1e10f : -1.0f;  // -1: never a candidate, fminf keeps it at -1
-      sx[i * kFpsThreads + tid] = x;
-      sy[i * kFpsThreads + tid] = y;
-      sz[i * kFpsThreads + tid] = z;
+  for (int i = 0; i < PTS; ++i) {
+    const int k = g + i * T;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool valid = false;
+    if (k < n) {
+      x = xyz[k * 3 + 0];
+      y = xyz[k * 3 + 1];
+      z = xyz[k * 3 + 2];
+      valid = !(static_cast<double>(sq3(x, y, z)) <= 1e-3);  // sampling_gpu.cu:105-106
     }
-#pragma unroll
-    for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], x0, y0, z0), pt[i]);  // sample 0
+    px[i] = x; py[i] = y; pz[i] = z;
+    pt[i] = valid ? 1e10f : -1.0f;  // -1: never a candidate, fminf keeps it at -1
+    sx[i * kFpsThreads + tid] = x;
+    sy[i * kFpsThreads + tid] = y;
+    sz[i * kFpsThreads + tid] = z;
   }
-  if (tid == 0) {
-    S.pub[0] = 0u;
-    S.pub[1] = 0u;
-    if (cs > 1) {
+  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
+  if (writer) {
+    idxs[0] = 0;
+    if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
+  }
+  if (cs > 1) {
+    if (tid == 0) {
       mbar_init(&S.bar[0], 1);
       mbar_init(&S.bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       mbar_arrive_expect_tx(&S.bar[0], cs * kCand2Bytes);
       mbar_arrive_expect_tx(&S.bar[1], cs * kCand2Bytes);
     }
+    cluster_sync_all();
   }
-  __syncthreads();
-  if (cs > 1) cluster_sync_all();
-
-  int j = 1;  // next output slot (every thread tracks it)
-  if (owner) {
-    // =============================== owner warps ===============================
-    for (int round = 0; j < m; ++round) {
-      const int p = round & 1;
-      // the thread's best / runner-up (every pick so far is already applied to pt[])
-      float best = -2.0f, second = -2.0f;
-      int ib = 0;
 #pragma unroll
-      for (int i = 0; i < PTS; ++i) {
-        const float t = pt[i];
-        if (t > best) { second = best; best = t; ib = i; }  // strict '>': lowest i (lowest rank in the thread) wins ties
-        else second = fmaxf(second, t);
-      }
-      // warp level: exact arg-max + bound over the warp's other points
-      const int kb = fps_key(best), ks = fps_key(second);
-      const int kmine = g + ib * T;
+  for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], x0, y0, z0), pt[i]);  // sample 0
+
+  int j = 1;  // next output slot
+  for (int round = 0; j < m; ++round) {
+    const int p = round & 1;
+    // ---- the thread's best / runner-up (every pick so far is already applied to pt[]) ----
+    float best = -2.0f, second = -2.0f;
+    int ib = 0;
+#pragma unroll
+    for (int i = 0; i < PTS; ++i) {
+      const float t = pt[i];
+      if (t > best) { second = best; best = t; ib = i; }  // strict '>': lowest i (lowest rank in the thread) wins ties
+      else second = fmaxf(second, t);
+    }
+    // ---- warp level: exact arg-max + bound over the warp's other points ----
+    const int kb = fps_key(best), ks = fps_key(second);
+    const int kmine = g + ib * T;
+    {
       const int src = warp_argmax_lane(kb, kmine, true, bs_log2);
       const int wb = __reduce_max_sync(FULL, lane == src ? ks : kb);
       if (lane == src) {
@@ -471,127 +447,94 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
         S.wz[p][warp] = sz[slot];
         S.wbound[p][warp] = wb;
       }
-      __syncwarp();
-      asm volatile("bar.arrive 2, %0;" ::"n"(kFpsCtaThreads) : "memory");  // candidates are in shared memory
-      // apply the round's picks as the resolver publishes them
-      int applied = 0;
-      while (true) {
-        const unsigned v = ld_acquire_shared(&S.pub[p]);
-        const int cnt = static_cast<int>(v & 0x00ffffffu);
-        for (; applied < cnt; ++applied) {
-          const float4 q = S.pick[p][applied];
-#pragma unroll
-          for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], q.x, q.y, q.z), pt[i]);
-        }
-        if (v & kPubDone) {
-          j = (v & kPubAllSkipped) ? m : j + cnt;
-          break;
-        }
+    }
+    __syncthreads();
+    // ---- candidates of this round, one per lane ----
+    int cd = INT_MIN, ck = 0, bmax;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    bool valid;
+    if (cs == 1) {
+      valid = lane < NW;
+      int wb = INT_MIN;
+      if (valid) {
+        const uint4 e = S.wcand[p][lane];
+        cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
+        cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.wz[p][lane];
+        wb = S.wbound[p][lane];
       }
-    }
-  } else {
-    // =============================== resolver warp ===============================
-    const bool writer = my_cta == 0 && lane == 0;
-    if (writer) {
-      idxs[0] = 0;
-      if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
-    }
-    for (int round = 0; j < m; ++round) {
-      const int p = round & 1;
-      asm volatile("bar.sync 2, %0;" ::"n"(kFpsCtaThreads) : "memory");
-      if (lane == 0) S.pub[p ^ 1] = 0u;  // next round's counter: every owner has left the round that used it
-      // ---- candidates of this round, one per lane ----
-      int cd = INT_MIN, ck = 0, bmax;
-      float cx = 0.f, cy = 0.f, cz = 0.f;
-      bool valid;
-      if (cs == 1) {
-        valid = lane < NW;
-        int wb = INT_MIN;
-        if (valid) {
+      bmax = __reduce_max_sync(FULL, wb);
+    } else {
+      if (warp < 2) {  // warp 0 forwards the CTA's best warp candidate (+ bound), warp 1 the runner-up
+        int d = INT_MIN, k = 0, wb = INT_MIN;
+        if (lane < NW) {
           const uint4 e = S.wcand[p][lane];
-          cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
-          cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.wz[p][lane];
+          d = static_cast<int>(e.x); k = static_cast<int>(e.y);
           wb = S.wbound[p][lane];
         }
-        bmax = __reduce_max_sync(FULL, wb);
-      } else {
-        {  // the CTA's two best warp candidates and the bound over everything else in the CTA -> every CTA
-          int d = INT_MIN, k = 0, wb = INT_MIN;
-          if (lane < NW) {
-            const uint4 e = S.wcand[p][lane];
-            d = static_cast<int>(e.x); k = static_cast<int>(e.y);
-            wb = S.wbound[p][lane];
-          }
-          const int src1 = warp_argmax_lane(d, k, lane < NW, bs_log2);
-          const bool rest = lane < NW && lane != src1;
-          const int m2 = __reduce_max_sync(FULL, rest ? d : INT_MIN);
-          const int src2 = __ffs(__ballot_sync(FULL, rest && d == m2)) - 1;
+        const int src1 = warp_argmax_lane(d, k, lane < NW, bs_log2);
+        const bool rest = lane < NW && lane != src1;
+        const int m2 = __reduce_max_sync(FULL, rest ? d : INT_MIN);
+        const int src2 = __ffs(__ballot_sync(FULL, rest && d == m2)) - 1;
+        if (warp == 0) {
           const int third = __reduce_max_sync(FULL, (rest && lane != src2) ? d : INT_MIN);
           const int cb = max(third, __reduce_max_sync(FULL, wb));
-          const int dst = lane & (kFpsMaxCluster - 1);
-          if (dst < cs) {  // lanes 0..cs-1 send the best, lanes 16..16+cs-1 the runner-up, to CTA `dst`
-            const int from = lane < kFpsMaxCluster ? src1 : src2;
-            const int slot = (lane < kFpsMaxCluster ? 0 : kFpsMaxCluster) + static_cast<int>(my_cta);
-            const uint4 w = S.wcand[p][from];
-            const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), dst);
-            st_async_v4(mapa_u32(smem_u32(&S.ccand[p][slot]), dst), rbar, w.x, w.y, w.z, w.w);
-            st_async_b32(mapa_u32(smem_u32(&S.cz[p][slot]), dst), rbar, __float_as_uint(S.wz[p][from]));
-            if (lane < kFpsMaxCluster)
-              st_async_b32(mapa_u32(smem_u32(&S.cbound[p][my_cta]), dst), rbar, static_cast<uint32_t>(cb));
+          if (lane < cs) {
+            const uint4 w = S.wcand[p][src1];
+            const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+            st_async_v4(mapa_u32(smem_u32(&S.ccand[p][my_cta]), lane), rbar, w.x, w.y, w.z, w.w);
+            st_async_b32(mapa_u32(smem_u32(&S.cz[p][my_cta]), lane), rbar, __float_as_uint(S.wz[p][src1]));
+            st_async_b32(mapa_u32(smem_u32(&S.cbound[p][my_cta]), lane), rbar, static_cast<uint32_t>(cb));
           }
+        } else if (lane < cs) {
+          const uint4 w = S.wcand[p][src2];
+          const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
+          st_async_v4(mapa_u32(smem_u32(&S.ccand[p][kFpsMaxCluster + my_cta]), lane), rbar, w.x, w.y, w.z, w.w);
+          st_async_b32(mapa_u32(smem_u32(&S.cz[p][kFpsMaxCluster + my_cta]), lane), rbar, __float_as_uint(S.wz[p][src2]));
         }
-        mbar_wait(&S.bar[p], (round >> 1) & 1);
-        if (lane == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCand2Bytes);  // re-arm for round + 2
-        valid = (lane & (kFpsMaxCluster - 1)) < cs;
-        if (valid) {
-          const uint4 e = S.ccand[p][lane];
-          cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
-          cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.cz[p][lane];
-        }
-        bmax = __reduce_max_sync(FULL, lane < cs ? S.cbound[p][lane] : INT_MIN);
       }
-      // ---- resolve as many picks as the bound allows ----
-      int npick = 0;
-      unsigned flags = kPubDone;
-      while (true) {
-        const int dm = __reduce_max_sync(FULL, valid ? cd : INT_MIN);
-        const unsigned eq = __ballot_sync(FULL, valid && cd == dm);
-        int src = __ffs(eq) - 1;
-        if (__popc(eq) > 1) {  // exact tie between candidates: reference order
-          const uint32_t r = (valid && cd == dm) ? rank_of(ck, bs_log2) : 0xffffffffu;
-          const uint32_t rm = __reduce_min_sync(FULL, r);
-          src = __ffs(__ballot_sync(FULL, r == rm)) - 1;
-        }
-        if (npick == 0) {
-          if (dm < 0) {  // no point is a candidate: the reference yields index 0 from here on
-            if (writer)
-              for (int t = j; t < m; ++t) {
-                idxs[t] = 0;
-                if (new_xyz) { new_xyz[t * 3 + 0] = x0; new_xyz[t * 3 + 1] = y0; new_xyz[t * 3 + 2] = z0; }
-              }
-            flags |= kPubAllSkipped;
-            break;
-          }
-        } else if (dm <= bmax) {
-          break;  // an outsider may beat or tie it: exact candidates are needed
-        }
-        const int kq = __shfl_sync(FULL, ck, src);
-        const float xq = __shfl_sync(FULL, cx, src), yq = __shfl_sync(FULL, cy, src), zq = __shfl_sync(FULL, cz, src);
-        if (lane == 0) {
-          S.pick[p][npick] = make_float4(xq, yq, zq, 0.f);
-          st_release_shared(&S.pub[p], static_cast<unsigned>(npick + 1));
-        }
-        if (writer) {
-          idxs[j + npick] = kq;
-          if (new_xyz) { new_xyz[(j + npick) * 3 + 0] = xq; new_xyz[(j + npick) * 3 + 1] = yq; new_xyz[(j + npick) * 3 + 2] = zq; }
-        }
-        ++npick;
-        if (j + npick >= m || npick == kFpsMaxPicks) break;
-        if (valid && cd >= 0) cd = __float_as_int(fminf(dist2(cx, cy, cz, xq, yq, zq), __int_as_float(cd)));
+      mbar_wait(&S.bar[p], (round >> 1) & 1);
+      if (tid == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCand2Bytes);  // re-arm for round + 2
+      valid = (lane & (kFpsMaxCluster - 1)) < cs;
+      if (valid) {
+        const uint4 e = S.ccand[p][lane];
+        cd = static_cast<int>(e.x); ck = static_cast<int>(e.y);
+        cx = __uint_as_float(e.z); cy = __uint_as_float(e.w); cz = S.cz[p][lane];
       }
-      if (lane == 0) st_release_shared(&S.pub[p], static_cast<unsigned>(npick) | flags);
-      j = (flags & kPubAllSkipped) ? m : j + npick;
+      bmax = __reduce_max_sync(FULL, lane < cs ? S.cbound[p][lane] : INT_MIN);
     }
+    // ---- resolve as many picks as the bound allows (every warp, identical result).  Each accepted pick is
+    // applied to the thread's resident points right away: that work is independent of the candidate chain, so
+    // the warps of an SM overlap one another's redux / shuffle latency with it. ----
+    int npick = 0;
+    while (true) {
+      const int src = warp_argmax_lane(cd, ck, valid, bs_log2);
+      const int dbest = __shfl_sync(FULL, cd, src);
+      if (npick == 0) {
+        if (dbest < 0) {  // no point is a candidate: the reference yields index 0 from here on
+          if (writer)
+            for (int t = j; t < m; ++t) {
+              idxs[t] = 0;
+              if (new_xyz) { new_xyz[t * 3 + 0] = x0; new_xyz[t * 3 + 1] = y0; new_xyz[t * 3 + 2] = z0; }
+            }
+          npick = m - j;
+          break;
+        }
+      } else if (dbest <= bmax) {
+        break;  // an outsider may beat or tie it: exact candidates are needed
+      }
+      const int kq = __shfl_sync(FULL, ck, src);
+      const float xq = __shfl_sync(FULL, cx, src), yq = __shfl_sync(FULL, cy, src), zq = __shfl_sync(FULL, cz, src);
+      if (writer) {
+        idxs[j + npick] = kq;
+        if (new_xyz) { new_xyz[(j + npick) * 3 + 0] = xq; new_xyz[(j + npick) * 3 + 1] = yq; new_xyz[(j + npick) * 3 + 2] = zq; }
+      }
+      ++npick;
+      if (valid && cd >= 0) cd = __float_as_int(fminf(dist2(cx, cy, cz, xq, yq, zq), __int_as_float(cd)));
+#pragma unroll
+      for (int i = 0; i < PTS; ++i) pt[i] = fminf(dist2(px[i], py[i], pz[i], xq, yq, zq), pt[i]);
+      if (j + npick >= m) break;
+    }
+    j += npick;
   }
   if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
 }
@@ -705,7 +648,7 @@ int launch_multipick(int b, int n, int m, int cs, int bs_log2, const float *xyz,
     cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   }
   void *args[] = {&n, &m, &cs, &bs_log2, &xyz, &idxs, &new_xyz};
-  return launch_cluster(kernel, b * cs, kFpsCtaThreads, smem, cs, stream, args);
+  return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
 }
 
 // PN2_FPS_MULTIPICK=0 selects the one-pick-per-round kernel (A/B measurements)

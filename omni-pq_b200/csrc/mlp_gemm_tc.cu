@@ -28,7 +28,7 @@ using namespace sm100;
 
 constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
 constexpr int TC_THREADS = 512;                    // 16 producer / epilogue warps
-constexpr int TC_CTA_THREADS = TC_THREADS + 32;    // + one warp whose lane 0 only issues the MMAs
+constexpr int TC_CTA_THREADS = TC_THREADS;         // thread 0 also issues the MMAs (after its warp's hand-over)
 constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
@@ -310,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs, nothing else
+  constexpr bool producer = true;
 
   const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
@@ -353,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
                         // that a gather's index load and the row loads that depend on it sit in different iterations
   auto col_a = [&](int kb) { return TRANS ? m0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
   auto col_b = [&](int kb) { return TRANS ? n0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
-  Raw ra[R], rb[R], ra_next[R], rb_next[R];
+  Raw da[2][R], db[2][R];  // two prefetch register sets, addressed with compile-time indices (loop unrolled by 2)
   if (producer) {
     if (TRANS) {
       make_ctx(0, ca, cb);
@@ -368,8 +368,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     if (num_kb > 0) {
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        ra[i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
-        rb[i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
+        da[0][i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
+        db[0][i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
       }
     }
     // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
@@ -383,81 +383,83 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, cta_id, 2, globaltimer_ns());
 
-  if (!producer) {
-    // ---- MMA warp: one thread waits for each stage to be written, issues its 12 MMAs and commits them to the
-    // stage's "empty" barrier.  It is NOT a producer: a thread that stages operands and then issues MMAs keeps
-    // its whole warp (and, through the block barrier, every producer) waiting while the tensor-pipe queue
-    // accepts them -- measured 1.3-1.9 us per k-block against 0.42 us of MMA time (profiles/c3_gemm_trace.txt).
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
-        tc_fence_after_sync();
-        const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
-        uint64_t a_hi, a_lo, b_hi, b_lo, step;
-        if (TRANS) {
-          a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
-          b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
-          b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
-          step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
-        } else {
-          a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
-          b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-          step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
-        }
-#pragma unroll
-        for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint64_t adv = step * ks;
-          mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-          mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-          mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
-        }
-        mma_commit(&empty_bar[s]);
-        if (kb == num_kb - 1) mma_commit(done_bar);
-      }
+  // ---- MMA issue (thread 0): wait until all 16 warps have written the stage, issue its 12 MMAs and commit them
+  // to the stage's "empty" barrier.  No block barrier: the other warps run ahead by up to the ring depth
+  // (a __syncthreads per k-block serialised staging and MMA issue: 1.3-1.9 us per k-block against 0.4 us of MMA
+  // time, profiles/c3_gemm_trace.txt).
+  auto issue_mmas = [&](int kb) {
+    const int s = kb % TC_STAGES;
+    mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
+    tc_fence_after_sync();
+    const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
+    uint64_t a_hi, a_lo, b_hi, b_lo, step;
+    if (TRANS) {
+      a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
+      b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
+      b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
+      step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
+    } else {
+      a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+      b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+      step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
     }
-  } else {
+#pragma unroll
+    for (int ks = 0; ks < TK / 8; ++ks) {
+      const uint64_t adv = step * ks;
+      mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+      mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+      mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+    }
+    mma_commit(&empty_bar[s]);
+    if (kb == num_kb - 1) mma_commit(done_bar);
+  };
+  {
     // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
     // per warp and reclaimed when the MMAs that read it have completed
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % TC_STAGES;
-      // 1. put the next k-block's loads in flight, then resolve the contexts of the block after it
-      if (kb + 1 < num_kb) {
+    for (int kb0 = 0; kb0 < num_kb; kb0 += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kb = kb0 + u;
+        if (kb >= num_kb) break;
+        const int s = kb % TC_STAGES;
+        // 1. put the next k-block's loads in flight (into the other register set: no copies, a move out of a
+        //    register with a load in flight would stall until the data is back)
+        if (kb + 1 < num_kb) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            da[u ^ 1][i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
+            db[u ^ 1][i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
+          }
+        }
+        // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
+        if (kb >= TC_STAGES) mbar_wait_guarded(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
+        unsigned char *st = tiles + s * STAGE_BYTES;
+        // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-          ra_next[i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
-          rb_next[i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
+          const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), da[u][i], coef_a, coef_ld_a, coef_base_a);
+          const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), db[u][i], coef_b, 128, coef_base_b);
+          float4 hi, lo;
+          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
+          split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
+          split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
+        }
+        fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (tid == 0) issue_mmas(kb);
+        // 4. contexts are computed values (cheap to move); resolve the block after the next one
+        if (TRANS) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+          make_ctx(kb + 2, na, nb);
         }
       }
-      // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
-      if (kb >= TC_STAGES) mbar_wait_guarded(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
-      unsigned char *st = tiles + s * STAGE_BYTES;
-      // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), ra[i], coef_a, coef_ld_a, coef_base_a);
-        const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), rb[i], coef_b, 128, coef_base_b);
-        float4 hi, lo;
-        split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-        split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-        *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-        split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-        split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-        *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
-      }
-      fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-      // 4. rotate the prefetch registers
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        ra[i] = ra_next[i];
-        rb[i] = rb_next[i];
-        if (TRANS) { ca[i] = na[i]; cb[i] = nb[i]; }
-      }
-      if (TRANS) make_ctx(kb + 2, na, nb);
     }
     float4 yv[8];
     tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
@@ -505,7 +507,7 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   __shared__ float red[2][TC_THREADS / 32][32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs (see gemm_tc_kernel)
+  constexpr bool producer = true;
   const int ntn = (g.N + TN - 1) / TN;
   const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
   const int m0 = m_tile * TM, n0 = n_tile * TN;
@@ -556,63 +558,67 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
-  if (!producer) {
-    if (lane == 0) {  // ---- MMA thread
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
-        mbar_wait_guarded(&full_a[sa], (kb >> 1) & 1);
-        mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
-        tc_fence_after_sync();
-        const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-        const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
-        const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
-        if (g.debug != 1 || kb == 0) {
+  auto issue_mmas = [&](int kb) {  // thread 0, after its own warp's hand-over (see gemm_tc_kernel)
+    const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
+    mbar_wait_guarded(&full_a[sa], (kb >> 1) & 1);
+    mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
+    tc_fence_after_sync();
+    const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+    const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
+    const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+    if (g.debug != 1 || kb == 0) {
 #pragma unroll
-          for (int ks = 0; ks < TK / 8; ++ks) {
-            const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
-          }
-        }
-        mma_commit(&empty_bar[sa]);
-        if (kb == num_kb - 1) mma_commit(done_bar);
+      for (int ks = 0; ks < TK / 8; ++ks) {
+        const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+        mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+        mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+        mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
       }
     }
-  } else {
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int sa = kb & (BK_A_STAGES - 1);
-      // 1. A loads of k-block kb + DEPTH in flight
+    mma_commit(&empty_bar[sa]);
+    if (kb == num_kb - 1) mma_commit(done_bar);
+  };
+  {
+    // The prefetch register sets are addressed with compile-time indices (loop unrolled by the number of
+    // sets): rotating them with register copies would make every iteration wait for the loads it has just
+    // issued -- a move out of a register with a load in flight stalls until the data is back.
+    constexpr int NSET = DEPTH + 1;
+    for (int kb0 = 0; kb0 < num_kb; kb0 += NSET) {
 #pragma unroll
-      for (int i = 0; i < R; ++i)
-        rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
-      // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
-      if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
-      if (tid == 0 && kb + 2 < num_kb) {
-        const int s2 = (kb + 2) & (BK_B_STAGES - 1);
-        mbar_expect_tx(&full_b[s2], BK_B_BYTES);
-        bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
-      }
-      // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
-      unsigned char *st = ring_a + sa * BK_A_BYTES;
-      if (g.debug != 2) {
+      for (int u = 0; u < NSET; ++u) {
+        const int kb = kb0 + u;
+        if (kb >= num_kb) break;
+        const int sa = kb & (BK_A_STAGES - 1);
+        // 1. A loads of k-block kb + DEPTH in flight
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
-          float4 hi, lo;
-          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+        for (int i = 0; i < R; ++i)
+          rr[(u + DEPTH) % NSET][i] =
+              fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
+        // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
+        if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
+        if (tid == 0 && kb + 2 < num_kb) {
+          const int s2 = (kb + 2) & (BK_B_STAGES - 1);
+          mbar_expect_tx(&full_b[s2], BK_B_BYTES);
+          bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
         }
+        // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
+        unsigned char *st = ring_a + sa * BK_A_BYTES;
+        if (g.debug != 2) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[u][i], coef_a, TC_KMAX, 0);
+            float4 hi, lo;
+            split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+            split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+            *reinterpret_cast<float4 *>(st + off[i]) = hi;
+            *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+        if (tid == 0) issue_mmas(kb);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_a[sa]);
-#pragma unroll
-      for (int d = 0; d < DEPTH; ++d)
-#pragma unroll
-        for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
     }
     float4 yv[8];
     tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
@@ -639,9 +645,9 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
 // the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc): no shared-memory traffic and no proxy fence for
 // A, 6 A stages in the 384 TMEM columns next to the accumulator, and all of shared memory for a 6-stage ring
 // of the bulk-copied weight image.  Shared-memory traffic per k-block drops from 160 KB to 80 KB.
-// Warps 0-15: producers + epilogue, warp 16: MMA issue (lane 0), warp 17: weight-stage loader (lane 0).
+// All 16 warps are producers + epilogue; thread 0 additionally loads the weight stages and issues the MMAs.
 constexpr int TS_A_STAGES = 6, TS_B_STAGES = 6;
-constexpr int TS_THREADS = TC_THREADS + 64;
+constexpr int TS_THREADS = TC_THREADS;
 constexpr uint32_t TS_TMEM_COLS = 512, TS_A_COL0 = 128, TS_A_STAGE_COLS = 64;  // per stage: 32 hi + 32 lo columns
 constexpr int TS_RING = TS_B_STAGES * BK_B_BYTES;
 constexpr int TS_SMEM = TS_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
@@ -662,7 +668,7 @@ gemm_tc_ts_kernel(const __grid_constant__ GemmArgs g) {
   __shared__ float red[2][TC_THREADS / 32][32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp < TC_THREADS / 32;
+  constexpr bool producer = true;
   const int ntn = (g.N + TN - 1) / TN;
   const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
   const int m0 = m_tile * TM, n0 = n_tile * TN;
@@ -708,65 +714,67 @@ gemm_tc_ts_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
-  if (warp == TC_THREADS / 32 + 1) {
-    if (lane == 0) {  // ---- weight loader: one 32 KB bulk copy per k-block, up to 6 in flight
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TS_B_STAGES;
-        if (kb >= TS_B_STAGES) mbar_wait_guarded(&empty_b[s], ((kb / TS_B_STAGES) - 1) & 1);
-        mbar_expect_tx(&full_b[s], BK_B_BYTES);
-        bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
-      }
-    }
-  } else if (warp == TC_THREADS / 32) {
-    if (lane == 0) {  // ---- MMA thread
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int sa = kb % TS_A_STAGES, sb = kb % TS_B_STAGES;
-        mbar_wait_guarded(&full_a[sa], (kb / TS_A_STAGES) & 1);
-        mbar_wait_guarded(&full_b[sb], (kb / TS_B_STAGES) & 1);
-        tc_fence_after_sync();
-        const uint32_t a_hi = tmem_d + TS_A_COL0 + sa * TS_A_STAGE_COLS, a_lo = a_hi + 32;
-        const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-        const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+  // thread 0 also loads the weight stages (one 32 KB bulk copy per k-block, TS_B_LEAD blocks ahead) and issues the MMAs
+  constexpr int TS_B_LEAD = TS_B_STAGES - 2;  // the stage being refilled was read two k-blocks ago: its MMAs are done
+  auto load_b = [&](int kb) {
+    const int s = kb % TS_B_STAGES;
+    if (kb >= TS_B_STAGES) mbar_wait_guarded(&empty_b[s], ((kb / TS_B_STAGES) - 1) & 1);
+    mbar_expect_tx(&full_b[s], BK_B_BYTES);
+    bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
+  };
+  auto issue_mmas = [&](int kb) {
+    const int sa = kb % TS_A_STAGES, sb = kb % TS_B_STAGES;
+    mbar_wait_guarded(&full_a[sa], (kb / TS_A_STAGES) & 1);
+    mbar_wait_guarded(&full_b[sb], (kb / TS_B_STAGES) & 1);
+    tc_fence_after_sync();
+    const uint32_t a_hi = tmem_d + TS_A_COL0 + sa * TS_A_STAGE_COLS, a_lo = a_hi + 32;
+    const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+    const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-          mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
-          mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, idesc, true);
-          mma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, idesc, true);
-        }
-        mma_commit(&empty_a[sa]);
-        mma_commit(&empty_b[sb]);
-        if (kb == num_kb - 1) mma_commit(done_bar);
-      }
+    for (int ks = 0; ks < TK / 8; ++ks) {
+      const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+      mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
+      mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, idesc, true);
+      mma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, idesc, true);
     }
-  } else {
+    mma_commit(&empty_a[sa]);
+    mma_commit(&empty_b[sb]);
+    if (kb == num_kb - 1) mma_commit(done_bar);
+  };
+  if (tid == 0)
+    for (int kb = 0; kb < TS_B_LEAD && kb < num_kb; ++kb) load_b(kb);
+  {
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + TS_A_COL0 + cgrp * 8;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int sa = kb % TS_A_STAGES;
+    constexpr int NSET = DEPTH + 1;  // compile-time register-set indices, see gemm_tc_bulk_kernel
+    for (int kb0 = 0; kb0 < num_kb; kb0 += NSET) {
 #pragma unroll
-      for (int j = 0; j < R; ++j) rr[DEPTH][j] = fetch_raw<AKIND>(g.A, ca, col_of(kb + DEPTH, j));
-      if (kb >= TS_A_STAGES) {
-        mbar_wait_guarded(&empty_a[sa], ((kb / TS_A_STAGES) - 1) & 1);
-        tc_fence_after_sync();
+      for (int u = 0; u < NSET; ++u) {
+        const int kb = kb0 + u;
+        if (kb >= num_kb) break;
+        const int sa = kb % TS_A_STAGES;
+#pragma unroll
+        for (int j = 0; j < R; ++j) rr[(u + DEPTH) % NSET][j] = fetch_raw<AKIND>(g.A, ca, col_of(kb + DEPTH, j));
+        if (tid == 0 && kb + TS_B_LEAD < num_kb) load_b(kb + TS_B_LEAD);
+        if (kb >= TS_A_STAGES) {
+          mbar_wait_guarded(&empty_a[sa], ((kb / TS_A_STAGES) - 1) & 1);
+          tc_fence_after_sync();
+        }
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const float4 v = apply_raw<AKIND>(g.A, ca, kb * TK + cgrp * 8 + 4 * j, rr[u][j], coef_a, TC_KMAX, 0);
+          split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+        }
+        const uint32_t dst = lane_base + sa * TS_A_STAGE_COLS;
+        tmem_st8(dst, hi);
+        tmem_st8(dst + 32, lo);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+        if (tid == 0) issue_mmas(kb);
       }
-      float hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const float4 v = apply_raw<AKIND>(g.A, ca, kb * TK + cgrp * 8 + 4 * j, rr[0][j], coef_a, TC_KMAX, 0);
-        split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-        split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
-      }
-      const uint32_t dst = lane_base + sa * TS_A_STAGE_COLS;
-      tmem_st8(dst, hi);
-      tmem_st8(dst + 32, lo);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_a[sa]);
-#pragma unroll
-      for (int d = 0; d < DEPTH; ++d)
-#pragma unroll
-        for (int j = 0; j < R; ++j) rr[d][j] = rr[d + 1][j];
     }
     float4 yv[8];
     tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
