@@ -28,7 +28,7 @@ using namespace sm100;
 
 constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
 constexpr int TC_THREADS = 512;                    // 16 producer / epilogue warps
-constexpr int TC_CTA_THREADS = TC_THREADS;         // thread 0 also issues the MMAs (after its warp's hand-over)
+constexpr int TC_CTA_THREADS = TC_THREADS + 32;    // + one warp whose lane 0 only issues the MMAs
 constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
 constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
@@ -282,7 +282,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
 // out + blockIdx.z * out_split_stride.
 // Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
 // 128-bit access touches 4 lines instead of 32.
-template <int AKIND, int BKIND, bool TRANS, int EPI>
+template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
 __global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
@@ -310,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-  constexpr bool producer = true;
+  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs, nothing else
 
   const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
   const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
@@ -383,8 +383,9 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, cta_id, 2, globaltimer_ns());
 
-  // ---- MMA issue (thread 0): wait until all 16 warps have written the stage, issue its 12 MMAs and commit them
-  // to the stage's "empty" barrier.  No block barrier: the other warps run ahead by up to the ring depth
+  // ---- MMA issue (lane 0 of warp 16, which does nothing else): wait until all 16 producer warps have written
+  // the stage, issue its 12 MMAs and commit them to the stage's "empty" barrier.  No block barrier, and the
+  // issuing thread is not a producer: a thread that stages operands and issues MMAs holds its warp back
   // (a __syncthreads per k-block serialised staging and MMA issue: 1.3-1.9 us per k-block against 0.4 us of MMA
   // time, profiles/c3_gemm_trace.txt).
   auto issue_mmas = [&](int kb) {
@@ -413,12 +414,20 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     mma_commit(&empty_bar[s]);
     if (kb == num_kb - 1) mma_commit(done_bar);
   };
-  {
+  if (!producer) {
+    if (lane == 0)
+      for (int kb = 0; kb < num_kb; ++kb) issue_mmas(kb);
+  } else {
     // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
     // per warp and reclaimed when the MMAs that read it have completed
-    for (int kb0 = 0; kb0 < num_kb; kb0 += 2) {
+    // ROT = false: the two prefetch register sets are addressed with compile-time indices (loop unrolled by 2);
+    // ROT = true: one loop body, the sets are rotated with register copies (fewer live registers, but the copy
+    // waits for the load it has just issued).  PN2_TC_ROT selects; both are kept until one is measured better
+    // on every shape.
+    constexpr int NU = ROT ? 1 : 2;
+    for (int kb0 = 0; kb0 < num_kb; kb0 += NU) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const int kb = kb0 + u;
         if (kb >= num_kb) break;
         const int s = kb % TC_STAGES;
@@ -452,12 +461,15 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
         fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
-        if (tid == 0) issue_mmas(kb);
         // 4. contexts are computed values (cheap to move); resolve the block after the next one
         if (TRANS) {
 #pragma unroll
           for (int i = 0; i < R; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
           make_ctx(kb + 2, na, nb);
+        }
+        if (ROT) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) { da[0][i] = da[1][i]; db[0][i] = db[1][i]; }
         }
       }
     }
@@ -487,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
 // (register sets: current, +1, +2, +3).  A: 2-stage ring written by all 16 warps as before.
 // Tiles are numbered with the n-tile fastest so that the CTAs sharing a row tile run together and the second
 // one reads A from L2.
-constexpr int BK_A_STAGES = 2, BK_B_STAGES = 4;
+constexpr int BK_A_STAGES = 3, BK_B_STAGES = 3;
 constexpr int BK_A_BYTES = 2 * TILE_BYTES, BK_B_BYTES = 2 * TILE_BYTES;  // hi + lo
 constexpr int BK_RING = BK_A_STAGES * BK_A_BYTES + BK_B_STAGES * BK_B_BYTES;
 constexpr int BK_SMEM = BK_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
@@ -507,7 +519,7 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   __shared__ float red[2][TC_THREADS / 32][32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr bool producer = true;
+  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs (see gemm_tc_kernel)
   const int ntn = (g.N + TN - 1) / TN;
   const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
   const int m0 = m_tile * TM, n0 = n_tile * TN;
@@ -525,7 +537,7 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
     mbar_init(done_bar, 1);
     mbar_fence_init();
     fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
-    for (int kb = 0; kb < 2 && kb < num_kb; ++kb) {
+    for (int kb = 0; kb < BK_B_STAGES && kb < num_kb; ++kb) {
       mbar_expect_tx(&full_b[kb], BK_B_BYTES);
       bulk_g2s(ring_b + kb * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[kb]);
     }
@@ -538,7 +550,8 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   uint32_t off[R];
   RowCtx ca[R];
   // A prefetch: DEPTH k-blocks ahead of the one being staged (register sets rr[0] = current .. rr[DEPTH])
-  constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 2 : 3;  // DYPOOL carries 9 registers per chunk: 2 sets ahead fit
+  // k-blocks of A in flight per thread beyond the current one (96 registers with 17 warps; DYPOOL chunks carry 9)
+  constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 1 : 2;
   Raw rr[DEPTH + 1][R];
   if (producer) {
 #pragma unroll
@@ -558,10 +571,10 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
   const uint32_t tmem_d = *tmem_slot;
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
-  auto issue_mmas = [&](int kb) {  // thread 0, after its own warp's hand-over (see gemm_tc_kernel)
-    const int sa = kb & (BK_A_STAGES - 1), sb = kb & (BK_B_STAGES - 1);
-    mbar_wait_guarded(&full_a[sa], (kb >> 1) & 1);
-    mbar_wait_guarded(&full_b[sb], (kb >> 2) & 1);
+  auto issue_mmas = [&](int kb) {  // lane 0 of the MMA warp
+    const int sa = kb % BK_A_STAGES, sb = kb % BK_B_STAGES;
+    mbar_wait_guarded(&full_a[sa], (kb / BK_A_STAGES) & 1);
+    mbar_wait_guarded(&full_b[sb], (kb / BK_B_STAGES) & 1);
     tc_fence_after_sync();
     const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
     const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
@@ -578,7 +591,10 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
     mma_commit(&empty_bar[sa]);
     if (kb == num_kb - 1) mma_commit(done_bar);
   };
-  {
+  if (!producer) {
+    if (lane == 0)
+      for (int kb = 0; kb < num_kb; ++kb) issue_mmas(kb);
+  } else {
     // The prefetch register sets are addressed with compile-time indices (loop unrolled by the number of
     // sets): rotating them with register copies would make every iteration wait for the loads it has just
     // issued -- a move out of a register with a load in flight stalls until the data is back.
@@ -588,18 +604,20 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
       for (int u = 0; u < NSET; ++u) {
         const int kb = kb0 + u;
         if (kb >= num_kb) break;
-        const int sa = kb & (BK_A_STAGES - 1);
+        const int sa = kb % BK_A_STAGES;
         // 1. A loads of k-block kb + DEPTH in flight
 #pragma unroll
         for (int i = 0; i < R; ++i)
           rr[(u + DEPTH) % NSET][i] =
               fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
-        // 2. MMAs of k-block kb - 2 done: A stage sa and B stage (kb + 2) % 4 are free
-        if (kb >= BK_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((kb >> 1) - 1) & 1);
-        if (tid == 0 && kb + 2 < num_kb) {
-          const int s2 = (kb + 2) & (BK_B_STAGES - 1);
-          mbar_expect_tx(&full_b[s2], BK_B_BYTES);
-          bulk_g2s(ring_b + s2 * BK_B_BYTES, b_src + static_cast<size_t>(kb + 2) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s2]);
+        // 2. MMAs of k-block kb - 3 done: A stage sa is free, and so is the weight stage that k-block read, which
+        //    thread 0 refills with k-block kb (the first three were requested in the prologue)
+        if (kb >= BK_A_STAGES) {
+          mbar_wait_guarded(&empty_bar[sa], ((kb / BK_A_STAGES) - 1) & 1);
+          if (tid == 0) {
+            mbar_expect_tx(&full_b[sa], BK_B_BYTES);
+            bulk_g2s(ring_b + sa * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[sa]);
+          }
         }
         // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
         unsigned char *st = ring_a + sa * BK_A_BYTES;
@@ -617,7 +635,6 @@ gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_a[sa]);
-        if (tid == 0) issue_mmas(kb);
       }
     }
     float4 yv[8];
@@ -830,9 +847,9 @@ int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
   return check_launch("gemm_tc_bulk_kernel");
 }
 
-template <int AKIND, int BKIND, bool TRANS, int EPI>
-int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
-  auto kernel = gemm_tc_kernel<AKIND, BKIND, TRANS, EPI>;
+template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
+int launch_tc_rot(const GemmArgs &g, int splits, cudaStream_t stream) {
+  auto kernel = gemm_tc_kernel<AKIND, BKIND, TRANS, EPI, ROT>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -845,6 +862,16 @@ int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
   gemm_trace_target(&a.trace, &a.trace_cap);
   kernel<<<grid, TC_CTA_THREADS, TC_SMEM, stream>>>(a);
   return check_launch("gemm_tc_kernel");
+}
+
+template <int AKIND, int BKIND, bool TRANS, int EPI>
+int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
+  static const bool rot = [] {
+    const char *e = getenv("PN2_TC_ROT");
+    return e != nullptr && e[0] == '1';
+  }();
+  return rot ? launch_tc_rot<AKIND, BKIND, TRANS, EPI, true>(g, splits, stream)
+             : launch_tc_rot<AKIND, BKIND, TRANS, EPI, false>(g, splits, stream);
 }
 
 }  // namespace
@@ -877,10 +904,10 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     return e == nullptr || e[0] != '0';
   }();
   const bool use_bulk = bulk_on && g.b_img != nullptr;
-  // PN2_TC_TS=0 keeps the A operand in shared memory (gemm_tc_bulk_kernel)
+  // PN2_TC_TS=1 selects the A-in-tensor-memory variant (correct, but measured slower: profiles/c7_gemm_trace_ts.txt)
   static const bool ts_on = [] {
     const char *e = getenv("PN2_TC_TS");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';
   }();
 #define PN2_TC_CASE(AK, EP)                                                                     \
   if (akind == AK && epi == EP)                                                                 \
