@@ -255,6 +255,10 @@ pool_bwd_prep_kernel(int groups, int group, int ld, float *__restrict__ gz, cons
 constexpr int kFpThreads = 128;
 constexpr int kFpTile = 1024;
 
+// PPB = unknown points per CTA: 128 (one per thread) for large clouds; 32 for the backbone's FP modules (512 / 1024
+// unknown points), where phase 2 -- a warp blending its points' rows one after the other, ~1 us of dependent row
+// loads each -- is the whole run time and 4 CTAs of 128 points left it at 60 us (profiles/r1_ncu_rest.json).
+template <int PPB>
 __global__ void __launch_bounds__(kFpThreads)
 fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restrict__ unknown,
                       const float *__restrict__ known, const float *__restrict__ known_pm, float *__restrict__ out,
@@ -265,8 +269,8 @@ fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restri
   const int b = blockIdx.y;
   unknown += static_cast<size_t>(b) * n * 3;
   known += static_cast<size_t>(b) * m * 3;
-  const int j = blockIdx.x * kFpThreads + threadIdx.x;
-  const bool live = j < n;
+  const int j = blockIdx.x * PPB + threadIdx.x;
+  const bool live = j < n && threadIdx.x < PPB;
   const int jj = live ? j : n - 1;
   const float ux = unknown[jj * 3 + 0], uy = unknown[jj * 3 + 1], uz = unknown[jj * 3 + 2];
   float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
@@ -277,7 +281,7 @@ fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restri
     for (int i = threadIdx.x; i < tn * 3; i += kFpThreads) tile[i] = known[base * 3 + i];
     __syncthreads();
 #pragma unroll 4
-    for (int k = 0; k < tn; ++k) {
+    for (int k = 0; k < (threadIdx.x < PPB ? tn : 0); ++k) {
       const float d = dist2(ux, uy, uz, tile[k * 3 + 0], tile[k * 3 + 1], tile[k * 3 + 2]);
       if (d < b3) {
         const int kk = base + k;
@@ -302,11 +306,12 @@ fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restri
     wo[0] = w1; wo[1] = w2; wo[2] = w3;
   }
   __syncthreads();
-  // phase 2: each warp blends the rows of its 32 points, one point at a time, lanes across channels
+  // phase 2: each warp blends the rows of its PPB/4 points, one point at a time, lanes across channels
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float *kp = known_pm + static_cast<size_t>(b) * m * ld_known;
-  for (int p = 0; p < 32; ++p) {
-    const int t = warp * 32 + p, jp = blockIdx.x * kFpThreads + t;
+  constexpr int PPW = PPB / (kFpThreads / 32);
+  for (int p = 0; p < PPW; ++p) {
+    const int t = warp * PPW + p, jp = blockIdx.x * PPB + t;
     if (jp >= n) break;
     const float *ra = kp + static_cast<size_t>(s_idx[t][0]) * ld_known;
     const float *rb = kp + static_cast<size_t>(s_idx[t][1]) * ld_known;
@@ -447,9 +452,15 @@ PN2_EXPORT int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, cons
               "pn2_fp_interpolate: bad extents b=%d n=%d m=%d c=%d ld_known=%d ldo=%d", b, n, m, c, ld_known, ldo);
   if (b == 0 || n == 0) return PN2_OK;
   PN2_REQUIRE(unknown && known && known_pm && out && idx && weight && b <= 65535, "pn2_fp_interpolate: null pointer");
-  dim3 grid((n + kFpThreads - 1) / kFpThreads, b);
-  fp_interpolate_kernel<<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, ld_known, unknown, known,
-                                                                                  known_pm, out, ldo, idx, weight);
+  if (static_cast<long long>(b) * n <= 16384) {
+    dim3 grid((n + 31) / 32, b);
+    fp_interpolate_kernel<32><<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, ld_known, unknown,
+                                                                                        known, known_pm, out, ldo, idx, weight);
+  } else {
+    dim3 grid((n + kFpThreads - 1) / kFpThreads, b);
+    fp_interpolate_kernel<kFpThreads><<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, m, c / 4, ld_known, unknown, known, known_pm, out, ldo, idx, weight);
+  }
   return check_launch("pn2_fp_interpolate");
 }
 

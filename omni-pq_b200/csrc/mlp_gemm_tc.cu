@@ -825,6 +825,171 @@ int launch_tc_ts(const GemmArgs &g, cudaStream_t stream) {
   return check_launch("gemm_tc_ts_kernel");
 }
 
+// ---- persistent form of gemm_tc_bulk_kernel -------------------------------------------------------------------
+// The per-CTA trace (profiles/r1_c8_gemm_trace.txt) shows 1.5 us of prologue (barrier init, TMEM allocation,
+// coefficient staging) and 0.9 us of CTA turnaround per 128x128 tile next to a 4-10 us main loop.  Here one CTA per
+// SM walks over the tiles (n-tile fastest, so neighbouring CTAs share A rows through L2): the prologue is paid
+// once, barriers / TMEM / coefficients live for the whole kernel, ring stages and barrier phases are indexed by a
+// running k-block counter.  A: 2-stage ring, weights: 4-stage ring, requested two k-blocks ahead inside a tile.
+// The epilogue scratch aliases the rings, hence one 512-thread barrier per tile after the epilogue.
+constexpr int PB_A_STAGES = 2, PB_B_STAGES = 4;
+constexpr int PB_RING = PB_A_STAGES * BK_A_BYTES + PB_B_STAGES * BK_B_BYTES;
+constexpr int PB_SMEM = PB_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
+
+template <int AKIND, int EPI>
+__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
+gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char *ring_a = tiles, *ring_b = tiles + PB_A_STAGES * BK_A_BYTES;
+  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + PB_RING);  // [2] MMAs of the k-block done (A stage, B stage)
+  uint64_t *full_a = empty_bar + PB_A_STAGES;                           // [2] A stage written (one arrival per producer warp)
+  uint64_t *full_b = full_a + PB_A_STAGES;                              // [4] weight stage landed
+  uint64_t *done_bar = full_b + PB_B_STAGES;                            // accumulator of the tile complete
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  float *coef_a = reinterpret_cast<float *>(tiles + PB_RING + 256);     // [3][TC_KMAX]
+  __shared__ float red[2][TC_THREADS / 32][32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs
+  const int ntn = (g.N + TN - 1) / TN;
+  const int ntiles = ((g.M + TM - 1) / TM) * ntn;
+  const int num_kb = (g.K + TK - 1) / TK;
+  trace_stamp(g, blockIdx.x, 0, smid());
+  trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
+
+  if (tid == 0) {
+    for (int s = 0; s < PB_A_STAGES; ++s) {
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_a[s], TC_THREADS / 32);
+    }
+    for (int s = 0; s < PB_B_STAGES; ++s) mbar_init(&full_b[s], 1);
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (producer) stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(TM, TN, false);
+  trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
+
+  if (!producer) {
+    if (lane == 0) {  // ---- MMA thread: the k-blocks of all of this CTA's tiles form one stream `it`
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int sa = it & (PB_A_STAGES - 1), sb = it & (PB_B_STAGES - 1);
+          mbar_wait_guarded(&full_a[sa], (it >> 1) & 1);  // the first block of a tile arrives only after every
+          mbar_wait_guarded(&full_b[sb], (it >> 2) & 1);  // warp has drained the previous accumulator
+          tc_fence_after_sync();
+          const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
+          const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
+          const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TK / 8; ++ks) {
+            const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
+            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+          }
+          mma_commit(&empty_bar[sa]);
+          if (kb == num_kb - 1) mma_commit(done_bar);
+        }
+      }
+    }
+  } else {
+    constexpr int R = TC_ROWS_PER_THREAD;
+    constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 1 : 2;  // k-blocks of A in flight beyond the current one
+    const int chunk = tid & 7, rsub = tid >> 3;
+    uint32_t off[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) off[i] = sw128_offset(rsub + 64 * i, chunk);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int m_tile = tile / ntn, n_tile = tile - m_tile * ntn;
+      const int m0 = m_tile * TM, n0 = n_tile * TN;
+      const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
+      auto load_b = [&](int kb, int stream) {  // thread 0: weight stage of k-block kb (stream index `stream`)
+        const int s = stream & (PB_B_STAGES - 1);
+        mbar_expect_tx(&full_b[s], BK_B_BYTES);
+        bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
+      };
+      if (tid == 0)
+        for (int kb = 0; kb < 2 && kb < num_kb; ++kb) load_b(kb, it + kb);  // every earlier MMA has completed (done_bar)
+      RowCtx ca[R];
+      Raw rr[DEPTH + 1][R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int sa = it & (PB_A_STAGES - 1);
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
+        // MMAs of stream block it - 2 done: A stage sa and weight stage (it + 2) % 4 are free
+        if (it >= PB_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((it >> 1) - 1) & 1);
+        if (tid == 0 && kb + 2 < num_kb) load_b(kb + 2, it + 2);
+        unsigned char *st = ring_a + sa * BK_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
+          float4 hi, lo;
+          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
+          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
+          *reinterpret_cast<float4 *>(st + off[i]) = hi;
+          *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+          for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
+      }
+      float4 yv[8];
+      tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
+      if (num_kb > 0) mbar_wait_guarded(done_bar, ti & 1);
+      tc_fence_after_sync();
+      tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
+      tc_fence_before_sync();   // this warp's TMEM reads are complete before the next tile's first MMA can be issued
+      producers_sync();         // the epilogue scratch aliases both rings
+    }
+  }
+  trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
+  trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
+  trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
+}
+
+template <int AKIND, int EPI>
+int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
+  auto kernel = gemm_tc_pbulk_kernel<AKIND, EPI>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM);
+    configured_dev = dev;
+  }
+  const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  GemmArgs a = g;
+  gemm_trace_target(&a.trace, &a.trace_cap);
+  kernel<<<grid, TC_CTA_THREADS, PB_SMEM, stream>>>(a);
+  return check_launch("gemm_tc_pbulk_kernel");
+}
+
 template <int AKIND, int EPI>
 int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
   auto kernel = gemm_tc_bulk_kernel<AKIND, EPI>;
@@ -911,10 +1076,16 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     const char *e = getenv("PN2_TC_TS");
     return e != nullptr && e[0] == '1';
   }();
+  // PN2_TC_PERSISTENT=0 launches one CTA per tile (gemm_tc_bulk_kernel) instead of the persistent form
+  static const bool persistent = [] {
+    const char *e = getenv("PN2_TC_PERSISTENT");
+    return e == nullptr || e[0] != '0';
+  }();
 #define PN2_TC_CASE(AK, EP)                                                                     \
   if (akind == AK && epi == EP)                                                                 \
     return !use_bulk ? launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream)                   \
-                     : ts_on ? launch_tc_ts<AK, EP>(g, stream) : launch_tc_bulk<AK, EP>(g, stream);
+           : ts_on   ? launch_tc_ts<AK, EP>(g, stream)                                          \
+           : persistent ? launch_tc_pbulk<AK, EP>(g, stream) : launch_tc_bulk<AK, EP>(g, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)
