@@ -1076,10 +1076,13 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     const char *e = getenv("PN2_TC_TS");
     return e != nullptr && e[0] == '1';
   }();
-  // PN2_TC_PERSISTENT=0 launches one CTA per tile (gemm_tc_bulk_kernel) instead of the persistent form
+  // PN2_TC_PERSISTENT=1 selects the persistent form.  Alone it is 13-17 % faster per GEMM
+  // (profiles/r1_c10_gemm_trace_persistent.txt), but inside the step it measured slower (4.11 vs 4.04 ms): a static
+  // grid of one CTA per SM cannot start on the 16 SMs the concurrent FPS cluster occupies, and those CTAs' tiles
+  // become a tail.  It needs a dynamic tile counter before it can be the default.
   static const bool persistent = [] {
     const char *e = getenv("PN2_TC_PERSISTENT");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';
   }();
 #define PN2_TC_CASE(AK, EP)                                                                     \
   if (akind == AK && epi == EP)                                                                 \
