@@ -832,6 +832,11 @@ int launch_tc_ts(const GemmArgs &g, cudaStream_t stream) {
 // once, barriers / TMEM / coefficients live for the whole kernel, ring stages and barrier phases are indexed by a
 // running k-block counter.  A: 2-stage ring, weights: 4-stage ring, requested two k-blocks ahead inside a tile.
 // The epilogue scratch aliases the rings, hence one 512-thread barrier per tile after the epilogue.
+// Tiles are handed out dynamically (thread 0 draws tickets from a global counter one tile ahead and publishes
+// them through shared memory + an mbarrier for the MMA thread): the geometry stream's FPS cluster occupies 16 SMs
+// for most of a forward pass, and with a static tile list the CTAs that start late became a tail.  The counter
+// resets itself: the CTA that draws the last of the ntiles + gridDim.x tickets knows nobody will draw again.
+__device__ int g_tile_counters[1024];
 constexpr int PB_A_STAGES = 2, PB_B_STAGES = 4;
 constexpr int PB_RING = PB_A_STAGES * BK_A_BYTES + PB_B_STAGES * BK_B_BYTES;
 constexpr int PB_SMEM = PB_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
@@ -846,9 +851,11 @@ gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
   uint64_t *full_a = empty_bar + PB_A_STAGES;                           // [2] A stage written (one arrival per producer warp)
   uint64_t *full_b = full_a + PB_A_STAGES;                              // [4] weight stage landed
   uint64_t *done_bar = full_b + PB_B_STAGES;                            // accumulator of the tile complete
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  uint64_t *tile_bar = done_bar + 1;                                    // next tile ticket published
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tile_bar + 1);
   float *coef_a = reinterpret_cast<float *>(tiles + PB_RING + 256);     // [3][TC_KMAX]
   __shared__ float red[2][TC_THREADS / 32][32];
+  __shared__ int ticket[2];  // ticket[ti & 1] = tile of this CTA's ti-th iteration (>= ntiles: stop)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs
@@ -865,9 +872,12 @@ gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
     }
     for (int s = 0; s < PB_B_STAGES; ++s) mbar_init(&full_b[s], 1);
     mbar_init(done_bar, 1);
+    mbar_init(tile_bar, 1);
     mbar_fence_init();
     fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
+    ticket[0] = atomicAdd(g.tile_counter, 1);
   }
+  const int last_ticket = ntiles + static_cast<int>(gridDim.x) - 1;
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
   if (producer) stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
   tc_fence_before_sync();
@@ -880,7 +890,9 @@ gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
   if (!producer) {
     if (lane == 0) {  // ---- MMA thread: the k-blocks of all of this CTA's tiles form one stream `it`
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        if (ti > 0) mbar_wait_guarded(tile_bar, (ti - 1) & 1);
+        if (ticket[ti & 1] >= ntiles) break;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int sa = it & (PB_A_STAGES - 1), sb = it & (PB_B_STAGES - 1);
           mbar_wait_guarded(&full_a[sa], (it >> 1) & 1);  // the first block of a tile arrives only after every
@@ -908,8 +920,17 @@ gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
     uint32_t off[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) off[i] = sw128_offset(rsub + 64 * i, chunk);
-    int it = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    int it = 0;
+    for (int ti = 0;; ++ti) {
+      const int tile = ticket[ti & 1];
+      if (tile >= ntiles) {
+        if (tid == 0 && tile == last_ticket) *g.tile_counter = 0;  // every CTA has drawn its last ticket
+        break;
+      }
+      if (tid == 0) {  // draw the next tile now; everybody reads it after this tile's closing barrier
+        ticket[(ti + 1) & 1] = atomicAdd(g.tile_counter, 1);
+        mbar_arrive(tile_bar);
+      }
       const int m_tile = tile / ntn, n_tile = tile - m_tile * ntn;
       const int m0 = m_tile * TM, n0 = n_tile * TN;
       const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
@@ -986,6 +1007,17 @@ int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
+  // one counter slot per launch in flight (a captured graph keeps replaying the slot it was captured with)
+  static thread_local int *counters = nullptr;
+  static thread_local int counters_dev = -1;
+  static thread_local unsigned next_slot = 0;
+  if (counters_dev != dev) {
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_tile_counters) != cudaSuccess) return check_launch("gemm_tc_pbulk_kernel(counters)");
+    counters = static_cast<int *>(p);
+    counters_dev = dev;
+  }
+  a.tile_counter = counters + (next_slot++ & 1023u);
   kernel<<<grid, TC_CTA_THREADS, PB_SMEM, stream>>>(a);
   return check_launch("gemm_tc_pbulk_kernel");
 }
@@ -1076,13 +1108,10 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     const char *e = getenv("PN2_TC_TS");
     return e != nullptr && e[0] == '1';
   }();
-  // PN2_TC_PERSISTENT=1 selects the persistent form.  Alone it is 13-17 % faster per GEMM
-  // (profiles/r1_c10_gemm_trace_persistent.txt), but inside the step it measured slower (4.11 vs 4.04 ms): a static
-  // grid of one CTA per SM cannot start on the 16 SMs the concurrent FPS cluster occupies, and those CTAs' tiles
-  // become a tail.  It needs a dynamic tile counter before it can be the default.
+  // PN2_TC_PERSISTENT=0 launches one CTA per tile (gemm_tc_bulk_kernel) instead of the persistent form
   static const bool persistent = [] {
     const char *e = getenv("PN2_TC_PERSISTENT");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr || e[0] != '0';
   }();
 #define PN2_TC_CASE(AK, EP)                                                                     \
   if (akind == AK && epi == EP)                                                                 \

@@ -103,6 +103,7 @@ struct GemmArgs {
   // development aid (pn2_debug_gemm_trace): per-CTA phase timestamps [smid, start, prologue, main loop, end, k-blocks]
   unsigned long long *trace;
   int trace_cap;
+  int *tile_counter;  // persistent GEMM: dynamic tile scheduler (self-resetting ticket counter)
   int debug;  // development aid (PN2_TC_DEBUG): 1 = skip the MMAs, 2 = skip operand staging (results are garbage)
 };
 
