@@ -44,9 +44,11 @@ int pn2_ref_block_size(int n);
 /* ---- K1  furthest_point_sampling(points, nsamples)   sampling.cpp:72-93, sampling_gpu.cu:74-234 --
  * xyz (b,n,3) -> idxs (b,m) int32.  Starts at index 0, skips points with |p|^2 <= 1e-3, breaks
  * ties exactly like the reference's 512-slot shared-memory tree.
- * temp: (b,n) fp32 scratch, only touched when n exceeds the register-resident capacity
- *       (pn2_fps_resident_capacity()); may be NULL otherwise.  Contents on return are unspecified
- *       (the reference leaves min-distances there; no caller reads them).
+ * temp: (b,n) fp32 scratch.  Required when n exceeds the register-resident capacity
+ *       (pn2_fps_resident_capacity()); optional otherwise -- when given and n <= 8192 it also enables the
+ *       prefix-order check (an input that already is in FPS order, as every level after the first is, is
+ *       verified in parallel and answered with 0..m-1 instead of being sampled again; same result).
+ *       Contents on return are unspecified (the reference leaves min-distances there; no caller reads them).
  * new_xyz: optional (b,m,3) output = xyz gathered at idxs (what gather_points does next in
  *       pointnet2_modules.py:238); pass NULL to skip. */
 int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idxs,

@@ -148,7 +148,7 @@ def furthest_point_sampling(points, nsamples, return_xyz=False):
         out = torch.zeros(b, nsamples, dtype=torch.int32, device=points.device)
         new_xyz = torch.empty(b, nsamples, 3, dtype=torch.float32, device=points.device) if return_xyz else None
         tmp = None
-        if n > lib.pn2_fps_resident_capacity():
+        if n > lib.pn2_fps_resident_capacity() or n <= 8192:  # streaming scratch / prefix-order check scratch
             tmp = torch.empty(b, n, dtype=torch.float32, device=points.device)
         _annotate(f"fps_kernel[{b}x{n}->{nsamples}]", nbytes=b * (12.0 * n + 16.0 * nsamples))
         _check(_fps(b, n, nsamples, _ptr(points), _ptr(tmp) if tmp is not None else None, _ptr(out),

@@ -137,3 +137,31 @@ int fps_multipick_emul(int n, int m, int cs, int bs, const float *xyz, int *idx)
   free(pt);
   return rounds;
 }
+
+/* CPU restatement of the prefix-order check (fps_prefix_diag_kernel + fps_prefix_check_kernel): returns 0 when the
+ * check passes (the kernel then answers 0..m-1), 1 when it raises the flag. */
+int fps_prefix_verify_emul(int n, int m, int bs, const float *xyz) {
+  int bs_log2 = 0;
+  while ((1 << (bs_log2 + 1)) <= bs) ++bs_log2;
+  float *diag = (float *)malloc(sizeof(float) * (size_t)m);
+  for (int j = 0; j < m; ++j) {
+    const float x = xyz[j * 3], y = xyz[j * 3 + 1], z = xyz[j * 3 + 2];
+    float d = ((double)sq3(x, y, z) <= 1e-3) ? -1.0f : 1e10f;
+    for (int i = 0; i < j; ++i) d = fminf(dist2(x, y, z, xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]), d);
+    diag[j] = d;
+  }
+  int flag = 0;
+  for (int k = 0; k < n && !flag; ++k) {
+    const float x = xyz[k * 3], y = xyz[k * 3 + 1], z = xyz[k * 3 + 2];
+    float d = ((double)sq3(x, y, z) <= 1e-3) ? -1.0f : 1e10f;
+    const uint32_t rk = rank_of(k, bs_log2);
+    for (int j = 1; j < m; ++j) {
+      d = fminf(dist2(x, y, z, xyz[(j - 1) * 3], xyz[(j - 1) * 3 + 1], xyz[(j - 1) * 3 + 2]), d);
+      const float dj = diag[j];
+      if (k == j) { if (dj < 0.f) { flag = 1; break; } }
+      else if (d >= 0.f && (d > dj || (d == dj && rk < rank_of(j, bs_log2)))) { flag = 1; break; }
+    }
+  }
+  free(diag);
+  return flag;
+}

@@ -27,6 +27,15 @@ def emul(tmp_path_factory):
     lib.fps_multipick_emul.restype = ctypes.c_int
     lib.fps_multipick_emul.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
 
+    lib.fps_prefix_verify_emul.restype = ctypes.c_int
+    lib.fps_prefix_verify_emul.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p]
+
+    def verify(xyz, m):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        n = xyz.shape[0]
+        bs = max(1, min(512, 2 ** int(math.log(n) / math.log(2.0))))
+        return lib.fps_prefix_verify_emul(n, m, bs, xyz.ctypes.data)
+
     def run(xyz, m, cs):
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         n = xyz.shape[0]
@@ -35,6 +44,7 @@ def emul(tmp_path_factory):
         rounds = lib.fps_multipick_emul(n, m, cs, bs, xyz.ctypes.data, idx.ctypes.data)
         assert rounds >= 0
         return idx, rounds
+    run.verify = verify
     return run
 
 
@@ -80,3 +90,29 @@ def test_multipick_scannet_levels_and_round_count(emul):
         if m == 2048:
             assert rounds < 2047 // 5, rounds
         xyz = torch.gather(xyz, 1, want.long()[..., None].expand(-1, -1, 3)).contiguous()
+
+
+def _fps_ordered(xyz, m):
+    inds = O.furthest_point_sample(xyz, m)
+    return torch.gather(xyz, 1, inds.long()[..., None].expand(-1, -1, 3)).contiguous()
+
+
+@pytest.mark.parametrize("name", cases.SMALL + ["c2_scannet"])
+def test_prefix_order_check_passes_only_when_the_answer_is_the_identity(name, emul):
+    """The prefix-order shortcut (fps.cu) answers 0..m-1 when its parallel check passes.  On unordered clouds and on
+    FPS-ordered ones (what every level after the first samples from) -- including duplicates, lattice ties and
+    skipped points, where the subset's tie-break ranks can break the identity -- the check must pass exactly when
+    the oracle's samples ARE 0..m-1."""
+    make, stages = cases.CASES[name]
+    xyz = make()
+    m0 = [s for s in stages if s[0] == "fps"][0][1]
+    passed = 0
+    for cloud, m in ((xyz, m0), (_fps_ordered(xyz, m0), m0 // 2), (_fps_ordered(xyz, m0), m0 - 1)):
+        want = O.furthest_point_sample(cloud, m).numpy()
+        for b in range(cloud.shape[0]):
+            identity = np.array_equal(want[b], np.arange(m, dtype=want.dtype))
+            ok = emul.verify(cloud[b].numpy(), m) == 0
+            assert ok == identity, (name, b, m, ok, identity)
+            passed += ok
+    if name in ("c1_uniform", "c2_scannet"):
+        assert passed >= 2  # the ordered levels of an ordinary cloud take the shortcut
