@@ -28,6 +28,7 @@ constexpr int kBqMaxSample = 128;
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz,
                   const float *__restrict__ xyz, int *__restrict__ idx) {
+  pdl_prologue();
   extern __shared__ int stage[];  // [kBqCentres][kBqWarps][nsample]
   __shared__ int counts[kBqCentres][kBqWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,7 +114,7 @@ PN2_EXPORT int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   PN2_REQUIRE(b <= 65535, "pn2_ball_query: b=%d exceeds the grid limit", b);
   dim3 grid((m + kBqCentres - 1) / kBqCentres, b);
   const size_t smem = sizeof(int) * kBqCentres * kBqWarps * static_cast<size_t>(nsample);  // <= 32 KB
-  ball_query_kernel<<<grid, kBqWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(n, m, radius, nsample, new_xyz, xyz,
+  pn2::launch(ball_query_kernel, dim3(grid), dim3(kBqWarps * 32), smem, static_cast<cudaStream_t>(stream), n, m, radius, nsample, new_xyz, xyz,
                                                                                      idx);
   return check_launch("pn2_ball_query");
 }

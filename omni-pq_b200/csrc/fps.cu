@@ -216,6 +216,7 @@ template <int PTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                     int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  pdl_prologue();
   constexpr int NW = kFpsThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FpsSmem2<NW> &S = *reinterpret_cast<FpsSmem2<NW> *>(smem_raw);
@@ -364,6 +365,7 @@ template <int PTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                      int *__restrict__ idxs, float *__restrict__ new_xyz, const int *__restrict__ identity_flag) {
+  pdl_prologue();
   constexpr int NW = kFpsThreads / 32;
   if (identity_flag != nullptr && identity_flag[blockIdx.x / cs] == 0) {
     // the prefix-order check passed for this cloud: the samples are 0 .. m-1 (every CTA of the cluster takes this
@@ -558,6 +560,7 @@ fps_multipick_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
 __global__ void __launch_bounds__(kStreamThreads, 1)
 fps_streaming_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
                      float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+  pdl_prologue();
   constexpr int NW = kStreamThreads / 32;
   __shared__ FpsSmem<NW> S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -638,6 +641,7 @@ constexpr int kPrefixThreads = 128;
 
 __global__ void __launch_bounds__(kPrefixThreads)
 fps_prefix_diag_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ diag, int *__restrict__ flag) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sp[];  // [m][3] prefix coordinates
   const int batch = blockIdx.y;
   xyz += static_cast<size_t>(batch) * n * 3;
@@ -656,6 +660,7 @@ fps_prefix_diag_kernel(int n, int m, const float *__restrict__ xyz, float *__res
 __global__ void __launch_bounds__(kPrefixThreads)
 fps_prefix_check_kernel(int n, int m, int bs_log2, const float *__restrict__ xyz, const float *__restrict__ diag,
                         int *__restrict__ flag) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sp[];  // [m][4]: x, y, z of point j, diag[j]
   const int batch = blockIdx.y;
   xyz += static_cast<size_t>(batch) * n * 3;
@@ -700,13 +705,15 @@ int launch_cluster(K kernel, int grid, int block, size_t smem, int cs, cudaStrea
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(kernel), args);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -802,10 +809,8 @@ PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz
       cudaFuncSetAttribute(fps_prefix_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrefixMaxN * 12);
       cudaFuncSetAttribute(fps_prefix_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrefixMaxN * 16);
     }
-    fps_prefix_diag_kernel<<<dim3((m + kPrefixThreads - 1) / kPrefixThreads, b), kPrefixThreads,
-                             static_cast<size_t>(m) * 12, stream>>>(n, m, xyz, diag, flag);
-    fps_prefix_check_kernel<<<dim3((n + kPrefixThreads - 1) / kPrefixThreads, b), kPrefixThreads,
-                              static_cast<size_t>(m) * 16, stream>>>(n, m, bs_log2, xyz, diag, flag);
+    pn2::launch(fps_prefix_diag_kernel, dim3(dim3((m + kPrefixThreads - 1) / kPrefixThreads, b)), dim3(kPrefixThreads), static_cast<size_t>(m) * 12, stream, n, m, xyz, diag, flag);
+    pn2::launch(fps_prefix_check_kernel, dim3(dim3((n + kPrefixThreads - 1) / kPrefixThreads, b)), dim3(kPrefixThreads), static_cast<size_t>(m) * 16, stream, n, m, bs_log2, xyz, diag, flag);
     if (int rc = check_launch("pn2_furthest_point_sampling(prefix check)")) return rc;
     identity_flag = flag;
   }

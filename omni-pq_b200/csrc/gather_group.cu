@@ -20,6 +20,7 @@ constexpr int kStrip = 8;  // channels per thread: amortises the index load, kee
 __global__ void __launch_bounds__(kThreads)
 column_gather_kernel(int c, int n, int cols, const float *__restrict__ points, const int *__restrict__ idx,
                      float *__restrict__ out) {
+  pdl_prologue();
   const int b = blockIdx.z;
   const int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= cols) return;
@@ -41,6 +42,7 @@ column_gather_kernel(int c, int n, int cols, const float *__restrict__ points, c
 __global__ void __launch_bounds__(kThreads)
 column_scatter_add_kernel(int c, int n, int cols, const float *__restrict__ grad_out, const int *__restrict__ idx,
                           float *__restrict__ grad_points) {
+  pdl_prologue();
   const int b = blockIdx.z;
   const int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= cols) return;
@@ -68,9 +70,9 @@ int launch_columns(bool scatter, const char *what, int b, int c, int n, long lon
   dim3 grid(static_cast<unsigned>((cols + kThreads - 1) / kThreads), (c + kStrip - 1) / kStrip, b);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (scatter)
-    column_scatter_add_kernel<<<grid, kThreads, 0, s>>>(c, n, static_cast<int>(cols), src, idx, dst);
+    pn2::launch(column_scatter_add_kernel, dim3(grid), dim3(kThreads), 0, s, c, n, static_cast<int>(cols), src, idx, dst);
   else
-    column_gather_kernel<<<grid, kThreads, 0, s>>>(c, n, static_cast<int>(cols), src, idx, dst);
+    pn2::launch(column_gather_kernel, dim3(grid), dim3(kThreads), 0, s, c, n, static_cast<int>(cols), src, idx, dst);
   return check_launch(what);
 }
 

@@ -24,6 +24,7 @@ constexpr int kNnTile = 1024;  // known points per shared-memory tile (12 KB)
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
                 float *__restrict__ dist2_out, int *__restrict__ idx_out) {
+  pdl_prologue();
   __shared__ float tile[kNnTile * 3];
   const int b = blockIdx.y;
   unknown += static_cast<size_t>(b) * n * 3;
@@ -68,6 +69,7 @@ constexpr int kIpStrip = 8;
 __global__ void __launch_bounds__(kIpThreads)
 three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, const int *__restrict__ idx,
                          const float *__restrict__ weight, float *__restrict__ out) {
+  pdl_prologue();
   const int b = blockIdx.z;
   const int j = blockIdx.x * kIpThreads + threadIdx.x;
   if (j >= n) return;
@@ -89,6 +91,7 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
 __global__ void __launch_bounds__(kIpThreads)
 three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out, const int *__restrict__ idx,
                               const float *__restrict__ weight, float *__restrict__ grad_points) {
+  pdl_prologue();
   const int b = blockIdx.z;
   const int j = blockIdx.x * kIpThreads + threadIdx.x;
   if (j >= n) return;
@@ -120,7 +123,7 @@ PN2_EXPORT int pn2_three_nn(int b, int n, int m, const float *unknown, const flo
   PN2_REQUIRE(unknown && dist2 && idx && (known || m == 0), "pn2_three_nn: null pointer");
   PN2_REQUIRE(b <= 65535, "pn2_three_nn: b=%d exceeds the grid limit", b);
   dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
-  three_nn_kernel<<<grid, kNnThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, m, unknown, known, dist2, idx);
+  pn2::launch(three_nn_kernel, dim3(grid), dim3(kNnThreads), 0, static_cast<cudaStream_t>(stream), n, m, unknown, known, dist2, idx);
   return check_launch("pn2_three_nn");
 }
 
@@ -132,7 +135,7 @@ PN2_EXPORT int pn2_three_interpolate(int b, int c, int m, int n, const float *po
   PN2_REQUIRE(points && idx && weight && out, "pn2_three_interpolate: null pointer");
   PN2_REQUIRE(b <= 65535 && (c + kIpStrip - 1) / kIpStrip <= 65535, "pn2_three_interpolate: grid limits exceeded");
   dim3 grid((n + kIpThreads - 1) / kIpThreads, (c + kIpStrip - 1) / kIpStrip, b);
-  three_interpolate_kernel<<<grid, kIpThreads, 0, static_cast<cudaStream_t>(stream)>>>(c, m, n, points, idx, weight, out);
+  pn2::launch(three_interpolate_kernel, dim3(grid), dim3(kIpThreads), 0, static_cast<cudaStream_t>(stream), c, m, n, points, idx, weight, out);
   return check_launch("pn2_three_interpolate");
 }
 
@@ -145,7 +148,7 @@ PN2_EXPORT int pn2_three_interpolate_grad(int b, int c, int n, int m, const floa
   PN2_REQUIRE(grad_out && idx && weight && grad_points, "pn2_three_interpolate_grad: null pointer");
   PN2_REQUIRE(b <= 65535 && (c + kIpStrip - 1) / kIpStrip <= 65535, "pn2_three_interpolate_grad: grid limits exceeded");
   dim3 grid((n + kIpThreads - 1) / kIpThreads, (c + kIpStrip - 1) / kIpStrip, b);
-  three_interpolate_grad_kernel<<<grid, kIpThreads, 0, static_cast<cudaStream_t>(stream)>>>(c, n, m, grad_out, idx, weight,
+  pn2::launch(three_interpolate_grad_kernel, dim3(grid), dim3(kIpThreads), 0, static_cast<cudaStream_t>(stream), c, n, m, grad_out, idx, weight,
                                                                                           grad_points);
   return check_launch("pn2_three_interpolate_grad");
 }

@@ -20,6 +20,7 @@ __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpre
 // are written as zeros.
 __global__ void __launch_bounds__(256)
 to_point_major_kernel(int c, int n, int ld, int stride, const float *__restrict__ src, float *__restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
@@ -40,6 +41,7 @@ to_point_major_kernel(int c, int n, int ld, int stride, const float *__restrict_
 
 __global__ void __launch_bounds__(256)
 to_channel_major_kernel(int c, int n, int stride, const float *__restrict__ src, float *__restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -102,6 +104,7 @@ __device__ __forceinline__ void total_of(const float *stats, int tiles, int np, 
 
 __global__ void __launch_bounds__(kStatCh * kStatLanes)
 bn_reduce_stats_kernel(int tiles, int c, int np, const float *__restrict__ stats, double *__restrict__ sums) {
+  pdl_prologue();
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
   double s1, s2;
   total_of(stats, tiles, np, ch, ch < c, s1, s2);
@@ -117,6 +120,7 @@ __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, doubl
                                    long long *__restrict__ nbt, float momentum, float eps, float *__restrict__ scale,
                                    float *__restrict__ shift, float *__restrict__ mean_out,
                                    float *__restrict__ invstd_out) {
+  pdl_prologue();
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
   // num_batches_tracked += 1 rides along when the momentum is fixed (nobody reads the counter then); with
   // momentum=None every channel reads it, so the host launches a separate increment afterwards
@@ -156,7 +160,8 @@ __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, doubl
   invstd_out[ch] = invstd;
 }
 
-__global__ void bn_bump_counter_kernel(long long *nbt) { *nbt += 1; }
+__global__ void bn_bump_counter_kernel(long long *nbt) {
+  pdl_prologue(); *nbt += 1; }
 
 __global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, double count,
                                        const float *__restrict__ stats, const double *__restrict__ sums,
@@ -164,6 +169,7 @@ __global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, d
                                        const float *__restrict__ invstd, float *__restrict__ ca,
                                        float *__restrict__ cb, float *__restrict__ cc, float *__restrict__ dgamma,
                                        float *__restrict__ dbeta) {
+  pdl_prologue();
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
   double s_dz = 0.0, s_dzy = 0.0;
   if (!sums) total_of(stats, tiles, np, ch, ch < c, s_dz, s_dzy);  // block-cooperative: before any return
@@ -196,6 +202,7 @@ __global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, d
 __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(int groups, int group, int ld, const float *__restrict__ y, const float *__restrict__ scale,
                     const float *__restrict__ shift, float *__restrict__ out_pm, unsigned char *__restrict__ arg) {
+  pdl_prologue();
   const int q = ld / 4;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(groups) * q) return;
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(128)
 pool_bwd_prep_kernel(int groups, int group, int ld, float *__restrict__ gz, const float *__restrict__ out_pm,
                      const unsigned char *__restrict__ arg, const float *__restrict__ y,
                      float *__restrict__ stats) {
+  pdl_prologue();
   const int g0 = blockIdx.x * kPrepGroups;
   for (int c4 = threadIdx.x * 4; c4 < ld; c4 += blockDim.x * 4) {
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -263,6 +271,7 @@ __global__ void __launch_bounds__(kFpThreads)
 fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restrict__ unknown,
                       const float *__restrict__ known, const float *__restrict__ known_pm, float *__restrict__ out,
                       int ldo, int *__restrict__ idx_out, float *__restrict__ w_out) {
+  pdl_prologue();
   __shared__ float tile[kFpTile * 3];
   __shared__ int s_idx[kFpThreads][3];
   __shared__ float s_w[kFpThreads][3];
@@ -335,6 +344,7 @@ __global__ void __launch_bounds__(256)
 fp_interpolate_grad_kernel(int n, int m, int c4n, const float *__restrict__ dout, int ldo,
                            const int *__restrict__ idx, const float *__restrict__ weight,
                            float *__restrict__ dknown_pm, int ld_known) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
@@ -373,9 +383,9 @@ static int transpose_launch(bool to_pm, int b, int c, int n, int ld, int stride,
   dim3 grid((n + 31) / 32, (cc + 31) / 32, b);
   PN2_REQUIRE(grid.y <= 65535, "%s: too many channels", what);
   if (to_pm)
-    to_point_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c, n, ld, stride, src, dst);
+    pn2::launch(to_point_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, ld, stride, src, dst);
   else
-    to_channel_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c, n, stride, src, dst);
+    pn2::launch(to_channel_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, stride, src, dst);
   return check_launch(what);
 }
 
@@ -388,7 +398,7 @@ PN2_EXPORT int pn2_to_channel_major(int b, int c, int n, int stride, const float
 
 PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream) {
   PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
-  bn_reduce_stats_kernel<<<(c + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, static_cast<cudaStream_t>(stream)>>>(tiles, c, np, stats, sums);
+  pn2::launch(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, stats, sums);
   return check_launch("pn2_bn_reduce_stats");
 }
 
@@ -400,12 +410,12 @@ PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double co
   PN2_REQUIRE(training ? ((stats || sums) && count > 0.0) : (running_mean && running_var),
               "pn2_bn_finalize: %s", training ? "training needs statistics and a positive count" : "eval needs running statistics");
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(np + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, s>>>(training, tiles, c, np, count, stats, sums, gamma, beta,
+  pn2::launch(bn_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, s, training, tiles, c, np, count, stats, sums, gamma, beta,
                                                        running_mean, running_var, num_batches_tracked, momentum, eps,
                                                        scale, shift, mean, invstd);
   if (int rc = check_launch("pn2_bn_finalize")) return rc;
   if (training && num_batches_tracked && running_mean && momentum < 0.f) {
-    bn_bump_counter_kernel<<<1, 1, 0, s>>>(num_batches_tracked);
+    pn2::launch(bn_bump_counter_kernel, dim3(1), dim3(1), 0, s, num_batches_tracked);
     return check_launch("pn2_bn_finalize(counter)");
   }
   return PN2_OK;
@@ -418,7 +428,7 @@ PN2_EXPORT int pn2_bn_relu_pool(int groups, int group, int c, int ld, const floa
   if (groups == 0) return PN2_OK;
   PN2_REQUIRE(y && scale && shift && out_pm, "pn2_bn_relu_pool: null pointer");
   const long long total = static_cast<long long>(groups) * (ld / 4);
-  bn_relu_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pn2::launch(bn_relu_pool_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       groups, group, ld, y, scale, shift, out_pm, arg);
   return check_launch("pn2_bn_relu_pool");
 }
@@ -431,7 +441,7 @@ PN2_EXPORT int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz
   if (tiles) *tiles = pn2_pool_bwd_tiles(groups);
   if (groups == 0) return PN2_OK;
   PN2_REQUIRE(gz && out_pm && y && stats && (arg || group == 1), "pn2_pool_bwd_prep: null pointer");
-  pool_bwd_prep_kernel<<<pn2_pool_bwd_tiles(groups), 128, 0, static_cast<cudaStream_t>(stream)>>>(groups, group, ld, gz,
+  pn2::launch(pool_bwd_prep_kernel, dim3(pn2_pool_bwd_tiles(groups)), dim3(128), 0, static_cast<cudaStream_t>(stream), groups, group, ld, gz,
                                                                                                 out_pm, arg, y, stats);
   return check_launch("pn2_pool_bwd_prep");
 }
@@ -441,7 +451,7 @@ PN2_EXPORT int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, doubl
                                    float *ca, float *cb, float *cc, float *dgamma, float *dbeta, void *stream) {
   PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && count > 0.0,
               "pn2_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(np + kStatCh - 1) / kStatCh, kStatCh * kStatLanes, 0, static_cast<cudaStream_t>(stream)>>>(
+  pn2::launch(bn_bwd_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), 
       training, tiles, c, np, count, stats, sums, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
   return check_launch("pn2_bn_bwd_finalize");
 }
@@ -454,11 +464,11 @@ PN2_EXPORT int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, cons
   PN2_REQUIRE(unknown && known && known_pm && out && idx && weight && b <= 65535, "pn2_fp_interpolate: null pointer");
   if (static_cast<long long>(b) * n <= 16384) {
     dim3 grid((n + 31) / 32, b);
-    fp_interpolate_kernel<32><<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, ld_known, unknown,
+    pn2::launch(fp_interpolate_kernel<32>, dim3(grid), dim3(kFpThreads), 0, static_cast<cudaStream_t>(stream), n, m, c / 4, ld_known, unknown,
                                                                                         known, known_pm, out, ldo, idx, weight);
   } else {
     dim3 grid((n + kFpThreads - 1) / kFpThreads, b);
-    fp_interpolate_kernel<kFpThreads><<<grid, kFpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    pn2::launch(fp_interpolate_kernel<kFpThreads>, dim3(grid), dim3(kFpThreads), 0, static_cast<cudaStream_t>(stream), 
         n, m, c / 4, ld_known, unknown, known, known_pm, out, ldo, idx, weight);
   }
   return check_launch("pn2_fp_interpolate");
@@ -470,7 +480,7 @@ PN2_EXPORT int pn2_fp_interpolate_grad(int b, int n, int m, int c, const float *
   if (b == 0 || n == 0) return PN2_OK;
   PN2_REQUIRE(dout && idx && weight && dknown_pm && b <= 65535, "pn2_fp_interpolate_grad: null pointer");
   dim3 grid((n + 7) / 8, b);
-  fp_interpolate_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, m, c / 4, dout, ldo, idx, weight,
+  pn2::launch(fp_interpolate_grad_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), n, m, c / 4, dout, ldo, idx, weight,
                                                                                 dknown_pm, ld_known);
   return check_launch("pn2_fp_interpolate_grad");
 }

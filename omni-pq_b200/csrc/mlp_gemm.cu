@@ -25,6 +25,7 @@ constexpr int BK = 16;
 template <int BM, int BN, int AKIND, bool ATRANS, int BKIND, int EPI>
 __global__ void __launch_bounds__((BM / 8) * (BN / 8), (BM == 128 ? 2 : 6))
 gemm_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_prologue();
   constexpr int TX = BN / 8, TY = BM / 8, THREADS = TX * TY;
   constexpr int A_LD = BM * BK / 4 / THREADS;  // float4 loads per thread per k-tile
   constexpr int B_LD = BN * BK / 4 / THREADS;
@@ -218,10 +219,10 @@ int launch_gemm(const GemmArgs &g, int splits, cudaStream_t stream, const char *
   // call that falls back to this kernel (K beyond the tensor-core kernel's coefficient staging) keeps that tiling
   if (big_tile(g.M, g.N) || (gemm_tc_enabled() && g.stats != nullptr)) {
     dim3 grid((g.M + 127) / 128, (g.N + 127) / 128, splits);
-    gemm_kernel<128, 128, AKIND, ATRANS, BKIND, EPI><<<grid, 256, 0, stream>>>(g);
+    pn2::launch(gemm_kernel<128, 128, AKIND, ATRANS, BKIND, EPI>, dim3(grid), dim3(256), 0, stream, g);
   } else {
     dim3 grid((g.M + 63) / 64, (g.N + 63) / 64, splits);
-    gemm_kernel<64, 64, AKIND, ATRANS, BKIND, EPI><<<grid, 64, 0, stream>>>(g);
+    pn2::launch(gemm_kernel<64, 64, AKIND, ATRANS, BKIND, EPI>, dim3(grid), dim3(64), 0, stream, g);
   }
   return check_launch(what);
 }
@@ -289,6 +290,7 @@ __device__ __forceinline__ void img_store(float *img, int cols, long long e, flo
 __global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np,
                                     const float *__restrict__ w, float *__restrict__ wt, float *__restrict__ wp,
                                     long long img_t, long long img_p) {
+  pdl_prologue();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < static_cast<long long>(kp) * np) {
     {  // wt[k][n]
@@ -322,6 +324,7 @@ __global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_p
 
 __global__ void wgrad_reduce_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, int splits,
                                     const float *__restrict__ ws, float *__restrict__ dw) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cout * kp) return;
   const int n = i / kp, k = i % kp;
@@ -372,7 +375,7 @@ PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_p
   long long total = static_cast<long long>(kp) * np;
   if (img_t > total) total = img_t;
   if (img_p > total) total = img_p;
-  prep_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pn2::launch(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p);
   return check_launch("pn2_mlp_prep_weights");
 }
@@ -523,6 +526,6 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
     if (rc) return rc;
   }
   const int total = cout * kp;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(cout, cin, xyz_first, feat_pad, kp, np, rows > 0 ? splits : 0, ws, dw);
+  pn2::launch(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, rows > 0 ? splits : 0, ws, dw);
   return check_launch("pn2_mlp_wgrad(reduce)");
 }

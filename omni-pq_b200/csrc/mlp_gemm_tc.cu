@@ -285,6 +285,7 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
 template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
 __global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + TC_STAGES * STAGE_BYTES);  // [TC_STAGES] MMAs of the stage done
@@ -507,6 +508,7 @@ constexpr int BK_SMEM = BK_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FL
 template <int AKIND, int EPI>
 __global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char *ring_a = tiles, *ring_b = tiles + BK_A_STAGES * BK_A_BYTES;
@@ -672,6 +674,7 @@ constexpr int TS_SMEM = TS_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FL
 template <int AKIND, int EPI>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 gemm_tc_ts_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char *ring_b = tiles;
@@ -821,7 +824,7 @@ int launch_tc_ts(const GemmArgs &g, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
-  kernel<<<grid, TS_THREADS, TS_SMEM, stream>>>(a);
+  pn2::launch(kernel, dim3(grid), dim3(TS_THREADS), TS_SMEM, stream, a);
   return check_launch("gemm_tc_ts_kernel");
 }
 
@@ -844,6 +847,7 @@ constexpr int PB_SMEM = PB_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FL
 template <int AKIND, int EPI>
 __global__ void __launch_bounds__(TC_CTA_THREADS, 1)
 gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char *ring_a = tiles, *ring_b = tiles + PB_A_STAGES * BK_A_BYTES;
@@ -1004,7 +1008,14 @@ int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
     configured_dev = dev;
   }
   const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  // PN2_TC_PERSISTENT_SPARE SMs are left to the geometry stream (FPS / ball query of the next level run underneath
+  // the MLP; a persistent grid on every SM would make them wait for a whole GEMM)
+  static const int spare = [] {
+    const char *e = getenv("PN2_TC_PERSISTENT_SPARE");
+    return e ? atoi(e) : 8;  // measured: 0 -> 4.11, 8 -> 3.92, 16 -> 3.93 ms per step (profiles/r1_bench_*spare*)
+  }();
+  const int sms = sm_count() - spare > 1 ? sm_count() - spare : 1;
+  const int grid = ntiles < sms ? ntiles : sms;
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
   // one counter slot per launch in flight (a captured graph keeps replaying the slot it was captured with)
@@ -1018,7 +1029,7 @@ int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
     counters_dev = dev;
   }
   a.tile_counter = counters + (next_slot++ & 1023u);
-  kernel<<<grid, TC_CTA_THREADS, PB_SMEM, stream>>>(a);
+  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), PB_SMEM, stream, a);
   return check_launch("gemm_tc_pbulk_kernel");
 }
 
@@ -1040,7 +1051,7 @@ int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
     return e ? atoi(e) : 0;
   }();
   a.debug = debug;
-  kernel<<<grid, TC_CTA_THREADS, BK_SMEM, stream>>>(a);
+  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), BK_SMEM, stream, a);
   return check_launch("gemm_tc_bulk_kernel");
 }
 
@@ -1057,7 +1068,7 @@ int launch_tc_rot(const GemmArgs &g, int splits, cudaStream_t stream) {
   dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, splits);
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
-  kernel<<<grid, TC_CTA_THREADS, TC_SMEM, stream>>>(a);
+  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), TC_SMEM, stream, a);
   return check_launch("gemm_tc_kernel");
 }
 

@@ -39,4 +39,32 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------
+// A step is ~160 small-to-medium kernels in two dependency chains; between two dependent kernels the GPU otherwise
+// idles for the launch latency of the second one.  Every kernel of the library starts with pdl_prologue(): it lets
+// the NEXT kernel of the stream be scheduled already (griddepcontrol.launch_dependents; that kernel's CTAs take
+// whatever SM resources are free) and then waits until the PREVIOUS kernel has completed and its writes are
+// visible (griddepcontrol.wait) before touching memory.  Launches go through pn2::launch(), which sets the
+// programmatic-stream-serialization attribute (PN2_PDL=0 switches it off; the device instructions are no-ops then).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 }  // namespace pn2

@@ -2,6 +2,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -34,6 +36,14 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached > 0 ? cached : 148;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("PN2_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 }  // namespace pn2
