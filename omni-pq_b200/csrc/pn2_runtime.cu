@@ -41,7 +41,7 @@ int sm_count() {
 bool pdl_enabled() {
   static const bool on = [] {
     const char *e = getenv("PN2_PDL");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';  // opt-in: correct (68/68 GPU tests) but measured slower, 4.21 vs 3.94 ms/step
   }();
   return on;
 }
