@@ -112,7 +112,7 @@ class Clocks:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -126,7 +126,10 @@ class Clocks:
     def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        # samples inside the timed region; a 30-step region lasts ~0.12 s, so fall back to the samples right around
+        # it (the GPU is busy with warm-up / the e2e loop there), then to the latest ones
+        rows = ([r for t, r in self.rows if t0 <= t <= t1] or [r for t, r in self.rows if t0 - 0.25 <= t <= t1 + 0.25]
+                or [r for _, r in self.rows[-3:]])
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -176,6 +179,7 @@ def main_ours(args):
     import _pn2
     from backbone import Pointnet2Backbone
 
+    clocks = Clocks(local_rank) if rank == 0 else None  # started early: nvidia-smi needs ~1 s before its first sample
     torch.manual_seed(0)
     model = Pointnet2Backbone(input_feature_dim=3).to(dev).train()
 
@@ -248,7 +252,6 @@ def main_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
-    clocks = Clocks(local_rank) if rank == 0 else None
     for it in range(args.warmup):
         step_resident(it)
     ms_total, t0, t1 = timed(step_resident, args.steps)

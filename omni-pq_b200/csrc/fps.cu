@@ -23,6 +23,7 @@
 //     (bitrev(k mod bs), k div bs) -- encoded below as `rank`; bs = pn2_ref_block_size(n);
 //   * if no point is a candidate (all skipped) the reference yields index 0.
 #include <limits.h>
+#include <math_constants.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -638,6 +639,7 @@ fps_streaming_kernel(int n, int m, int cs, int bs_log2, const float *__restrict_
 // j = 1 and pays ~10 us.  Only attempted for n <= kPrefixMaxN.
 constexpr int kPrefixMaxN = 8192;
 constexpr int kPrefixThreads = 128;
+constexpr int kPrefixPad = 8;  // steps per unrolled trip of the check kernel = padding rows behind the prefix
 
 __global__ void __launch_bounds__(kPrefixThreads)
 fps_prefix_diag_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ diag, int *__restrict__ flag) {
@@ -653,6 +655,7 @@ fps_prefix_diag_kernel(int n, int m, const float *__restrict__ xyz, float *__res
   if (j >= m) return;
   const float x = sp[j * 3 + 0], y = sp[j * 3 + 1], z = sp[j * 3 + 2];
   float d = (static_cast<double>(sq3(x, y, z)) <= 1e-3) ? -1.0f : 1e10f;  // sampling_gpu.cu:105-106
+#pragma unroll 8
   for (int i = 0; i < j; ++i) d = fminf(dist2(x, y, z, sp[i * 3 + 0], sp[i * 3 + 1], sp[i * 3 + 2]), d);
   diag[j] = d;
 }
@@ -665,11 +668,12 @@ fps_prefix_check_kernel(int n, int m, int bs_log2, const float *__restrict__ xyz
   const int batch = blockIdx.y;
   xyz += static_cast<size_t>(batch) * n * 3;
   diag += static_cast<size_t>(batch) * m;
-  for (int i = threadIdx.x; i < m; i += kPrefixThreads) {
-    sp[i * 4 + 0] = xyz[i * 3 + 0];
-    sp[i * 4 + 1] = xyz[i * 3 + 1];
-    sp[i * 4 + 2] = xyz[i * 3 + 2];
-    sp[i * 4 + 3] = diag[i];
+  for (int i = threadIdx.x; i < m + kPrefixPad; i += kPrefixThreads) {
+    const bool in = i < m;  // padding rows: a step nobody can lose (diag = +inf), so the loop below needs no tail
+    sp[i * 4 + 0] = in ? xyz[i * 3 + 0] : 0.f;
+    sp[i * 4 + 1] = in ? xyz[i * 3 + 1] : 0.f;
+    sp[i * 4 + 2] = in ? xyz[i * 3 + 2] : 0.f;
+    sp[i * 4 + 3] = in ? diag[i] : CUDART_INF_F;
   }
   __syncthreads();
   const int k = blockIdx.x * kPrefixThreads + threadIdx.x;
@@ -678,13 +682,17 @@ fps_prefix_check_kernel(int n, int m, int bs_log2, const float *__restrict__ xyz
   float d = (static_cast<double>(sq3(x, y, z)) <= 1e-3) ? -1.0f : 1e10f;
   const uint32_t rk = rank_of(k, bs_log2);
   bool bad = false;
-  for (int j = 1; j < m; ++j) {
-    const float4 q = *reinterpret_cast<const float4 *>(sp + (j - 1) * 4);
-    d = fminf(dist2(x, y, z, q.x, q.y, q.z), d);
-    const float dj = sp[j * 4 + 3];
-    if (k == j) bad |= dj < 0.f;                                            // a skipped point is never sampled
-    else if (d >= 0.f) bad |= d > dj || (d == dj && rk < rank_of(j, bs_log2));  // somebody else wins step j
-    if ((j & 63) == 0 && (bad || *reinterpret_cast<volatile int *>(flag + batch) != 0)) break;
+  for (int j0 = 1; j0 < m; j0 += kPrefixPad) {  // kPrefixPad steps per trip: their shared-memory loads overlap
+#pragma unroll
+    for (int u = 0; u < kPrefixPad; ++u) {
+      const int j = j0 + u;  // j >= m only touches the padding rows (after the last real step d is not used again)
+      const float4 q = *reinterpret_cast<const float4 *>(sp + (j - 1) * 4);
+      d = fminf(dist2(x, y, z, q.x, q.y, q.z), d);
+      const float dj = sp[j * 4 + 3];
+      if (k == j) bad |= dj < 0.f;                                              // a skipped point is never sampled
+      else if (d >= 0.f) bad |= d > dj || (d == dj && rk < rank_of(j, bs_log2));  // somebody else wins step j
+    }
+    if ((((j0 - 1) / kPrefixPad) & 7) == 0 && (bad || *reinterpret_cast<volatile int *>(flag + batch) != 0)) break;
   }
   if (bad) flag[batch] = 1;
 }
@@ -807,10 +815,10 @@ PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz
     static thread_local int configured_dev = -1;
     if (!configured_on(configured_dev)) {
       cudaFuncSetAttribute(fps_prefix_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrefixMaxN * 12);
-      cudaFuncSetAttribute(fps_prefix_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrefixMaxN * 16);
+      cudaFuncSetAttribute(fps_prefix_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kPrefixMaxN + kPrefixPad) * 16);
     }
     pn2::launch(fps_prefix_diag_kernel, dim3(dim3((m + kPrefixThreads - 1) / kPrefixThreads, b)), dim3(kPrefixThreads), static_cast<size_t>(m) * 12, stream, n, m, xyz, diag, flag);
-    pn2::launch(fps_prefix_check_kernel, dim3(dim3((n + kPrefixThreads - 1) / kPrefixThreads, b)), dim3(kPrefixThreads), static_cast<size_t>(m) * 16, stream, n, m, bs_log2, xyz, diag, flag);
+    pn2::launch(fps_prefix_check_kernel, dim3(dim3((n + kPrefixThreads - 1) / kPrefixThreads, b)), dim3(kPrefixThreads), static_cast<size_t>(m + kPrefixPad) * 16, stream, n, m, bs_log2, xyz, diag, flag);
     if (int rc = check_launch("pn2_furthest_point_sampling(prefix check)")) return rc;
     identity_flag = flag;
   }
