@@ -100,7 +100,7 @@ def main_reference(args):
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's ops are CUDA-only; its CPU path is the oracle restatement (oracle/) under the "
                     "reference's module glue, run on all host cores; steps bounded to keep the run short"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- clocks sampler -----------------------------------------------------------------------------------------------
@@ -354,7 +354,7 @@ def main_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def ref_gpu_run(args, dev):
@@ -401,7 +401,25 @@ def ref_gpu_run(args, dev):
         return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
 
+def _claim_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL's version banner, warnings) write to file descriptor 1
+    directly, so point fd 1 at stderr for the whole run and keep a private handle on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _claim_stdout()
     a = parse()
     if a.impl == "reference":
         main_reference(a)
