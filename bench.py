@@ -198,9 +198,9 @@ def main_ours(args):
     eager_net = Features(model)  # never graphed: kernel counting and the per-kernel CUDA-event pass
     net = Features(model)
     torch.cuda.synchronize()
-    count0 = _pn2.launch_count
+    count0 = _pn2.kernel_launches()
     eager_net(resident[0][None].repeat(args.batch, 1, 1)).sum().backward()  # one eager step: kernels per step
-    launches_per_step = _pn2.launch_count - count0
+    launches_per_step = _pn2.kernel_launches() - count0  # counted inside libpn2_b200.so, one per kernel launch
     model.zero_grad(set_to_none=True)
     graphed = False
     if not args.no_graph:

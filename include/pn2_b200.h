@@ -41,6 +41,10 @@ const char *pn2_last_error(void);
  * tie-break order of furthest point sampling, so it is part of the contract. */
 int pn2_ref_block_size(int n);
 
+/* Number of kernels this library has launched in the calling process so far (every launch goes through one
+ * helper); bench.py reports the per-step difference as `gpu_launches`. */
+long long pn2_kernel_launches(void);
+
 /* ---- K1  furthest_point_sampling(points, nsamples)   sampling.cpp:72-93, sampling_gpu.cu:74-234 --
  * xyz (b,n,3) -> idxs (b,m) int32.  Starts at index 0, skips points with |p|^2 <= 1e-3, breaks
  * ties exactly like the reference's 512-slot shared-memory tree.

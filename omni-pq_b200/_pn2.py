@@ -28,6 +28,13 @@ if not os.path.exists(LIB_PATH):
 lib = ctypes.CDLL(LIB_PATH)
 lib.pn2_last_error.restype = ctypes.c_char_p
 lib.pn2_version.restype = ctypes.c_int
+lib.pn2_kernel_launches.restype = ctypes.c_longlong
+
+
+def kernel_launches():
+    """Kernels launched by libpn2_b200.so in this process so far (counted inside the library)."""
+    return int(lib.pn2_kernel_launches())
+
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -722,6 +722,7 @@ int launch_cluster(K kernel, int grid, int block, size_t smem, int cs, cudaStrea
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  note_launch();
   cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(kernel), args);
   if (e != cudaSuccess) {
     cudaGetLastError();

@@ -53,6 +53,7 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool pdl_enabled();
+void note_launch();  // counts every kernel launch of the library (pn2_kernel_launches())
 
 template <typename... P, typename... A>
 inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args) {
@@ -66,6 +67,7 @@ inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t sm
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 

@@ -4,6 +4,8 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -38,6 +40,10 @@ int sm_count() {
   return cached > 0 ? cached : 148;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char *e = getenv("PN2_PDL");
@@ -49,6 +55,8 @@ bool pdl_enabled() {
 }  // namespace pn2
 
 PN2_EXPORT int pn2_version(void) { return 100; }
+
+PN2_EXPORT long long pn2_kernel_launches(void) { return pn2::launches(); }
 
 PN2_EXPORT const char *pn2_last_error(void) { return pn2::g_err; }
 
