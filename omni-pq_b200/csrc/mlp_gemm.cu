@@ -407,6 +407,10 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
     t.B = plain_rows(wp, np, kp, kp);
     t.b_img = wp + static_cast<size_t>(np) * kp;
     t.b_img_kblocks = (kp + 31) / 32;
+    if (smallk_eligible(a->kind, kp, np)) {
+      const int rc = smallk_forward_launch(&t, s);
+      if (rc != PN2_TC_UNSUPPORTED) return rc;
+    }
     const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
@@ -490,7 +494,9 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
 }
 
 PN2_EXPORT long long pn2_mlp_wgrad_workspace(int rows, int np, int kp) {
-  return static_cast<long long>(wgrad_splits(rows, np, kp)) * np * kp;
+  int splits = wgrad_splits(rows, np, kp);
+  if (smallk_eligible(PN2_ROWS_PLAIN, kp, np) && smallk_wgrad_splits(rows) > splits) splits = smallk_wgrad_splits(rows);
+  return static_cast<long long>(splits) * np * kp;
 }
 
 PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, int cin, int xyz_first, int feat_pad,
@@ -503,14 +509,22 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   PN2_REQUIRE(dy->rows == a->rows && ws && dw && cout <= dy->cols && cin <= a->cols, "pn2_mlp_wgrad: shapes disagree");
   const int np = dy->cols, kp = a->cols, rows = dy->rows;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  const int splits = wgrad_splits(rows, np, kp);
+  int splits = wgrad_splits(rows, np, kp);
   GemmArgs g = {};
   g.A = *dy; g.B = *a;
   g.M = np; g.N = kp; g.K = rows;
   g.k_per_split = ((rows + splits - 1) / splits + 31) / 32 * 32;  // multiple of both kernels' k-block
   g.out = ws; g.ldo = kp; g.out_split_stride = static_cast<long long>(np) * kp;
   int rc = PN2_TC_UNSUPPORTED;
-  if (rows > 0 && gemm_tc_enabled()) {
+  if (rows > 0 && dy->kind == PN2_ROWS_DY && smallk_eligible(a->kind, kp, np)) {  // first layers: K <= 16
+    GemmArgs k = g;
+    const int ks = smallk_wgrad_splits(rows);
+    k.k_per_split = (rows + ks - 1) / ks;
+    rc = smallk_wgrad_launch(&k, ks, s);
+    if (rc != PN2_TC_UNSUPPORTED && rc != PN2_OK) return rc;
+    if (rc == PN2_OK) splits = ks;
+  }
+  if (rows > 0 && rc == PN2_TC_UNSUPPORTED && gemm_tc_enabled()) {
     rc = gemm_tc_wgrad_launch(&g, splits, s);
     if (rc != PN2_TC_UNSUPPORTED && rc != PN2_OK) return rc;
   }

@@ -114,6 +114,11 @@ constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
+// first-layer kernels for K <= 16 (mlp_smallk.cu)
+bool smallk_eligible(int akind, int kp, int np);
+int smallk_wgrad_splits(int rows);
+int smallk_forward_launch(const void *gemm_args, cudaStream_t stream);
+int smallk_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 void gemm_trace_target(unsigned long long **buf, int *cap);
 
 }  // namespace pn2
