@@ -15,6 +15,8 @@
 // (256 threads, 8x8 register micro-tile, double-buffered shared memory, 128-bit loads everywhere) or
 // 64x64x16 when the problem would leave SMs idle; weight-gradient launches split the position
 // dimension across CTAs and reduce the partial tiles in a fixed order.
+#include <stdlib.h>
+
 #include "mlp_rows.cuh"
 
 namespace pn2 {
@@ -335,6 +337,32 @@ __global__ void wgrad_reduce_kernel(int cout, int cin, int xyz_first, int feat_p
   dw[static_cast<size_t>(n) * cin + c] = s;
 }
 
+// Same reduction with the slices spread over the warps of a block: lane = element (consecutive k, coalesced), warp w
+// sums slices w, w + nw, ... and the nw partials are combined in a fixed order through shared memory.  A thread per
+// element walking hundreds of 4 KB-strided slices one after the other was latency-bound (the 128 x 8 first-layer
+// gradient: ~100 us of a 125 us call).  Deterministic: the summation order depends on (splits, nw) only.
+__global__ void __launch_bounds__(512)
+wgrad_reduce_wide_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np, int splits,
+                         const float *__restrict__ ws, float *__restrict__ dw) {
+  pdl_prologue();
+  __shared__ float part[16][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int i = blockIdx.x * 32 + lane;  // element of the [cout][kp] gradient
+  const bool live = i < cout * kp;
+  const int n = live ? i / kp : 0, k = live ? i % kp : 0;
+  float s = 0.f;
+  if (live)
+    for (int z = warp; z < splits; z += nw) s += ws[(static_cast<size_t>(z) * np + n) * kp + k];
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp != 0 || !live) return;
+  const int c = orig_cin(k, cin, xyz_first, feat_pad);
+  if (c < 0) return;
+  float t = 0.f;
+  for (int w = 0; w < nw; ++w) t += part[w][lane];
+  dw[static_cast<size_t>(n) * cin + c] = t;
+}
+
 int wgrad_splits(int rows, int np, int kp) {
   if (gemm_tc_enabled()) {  // tcgen05 kernel: 128x128 tiles, 1 CTA/SM, position slices of >= 4 k-blocks of 32
     const long long t = ((np + 127) / 128) * ((kp + 127) / 128);
@@ -540,6 +568,18 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
     if (rc) return rc;
   }
   const int total = cout * kp;
-  pn2::launch(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, rows > 0 ? splits : 0, ws, dw);
+  static const bool wide = [] {
+    const char *e = getenv("PN2_WGRAD_REDUCE_WIDE");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int nsl = rows > 0 ? splits : 0;
+  if (wide && nsl > 2) {
+    int nw = 1;
+    while (nw < 16 && nw < nsl) nw *= 2;
+    pn2::launch(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,
+                ws, dw);
+  } else {
+    pn2::launch(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl, ws, dw);
+  }
   return check_launch("pn2_mlp_wgrad(reduce)");
 }
