@@ -573,7 +573,7 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
     return e == nullptr || e[0] != '0';
   }();
   const int nsl = rows > 0 ? splits : 0;
-  if (wide && nsl > 2) {
+  if (wide && nsl >= 64) {  // few, large slices (big outputs): the thread-per-element kernel is faster (measured)
     int nw = 1;
     while (nw < 16 && nw < nsl) nw *= 2;
     pn2::launch(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,

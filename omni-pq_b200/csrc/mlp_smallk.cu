@@ -10,7 +10,10 @@
 //   wgrad   : CTA = a slice of positions, lane = 4 dY channels, acc[4][kp] per thread, fixed-order cross-warp
 //             combine into ws[slice][np][kp]; the existing split reduction (+ channel permutation) finishes it.
 // Sources: A = PLAIN / GATHER (first layers), dY = DY (the layer above handed down dz; a single-layer MLP, whose dY
-// is DYPOOL, stays on the tensor-core path).  PN2_SMALLK=0 disables both.
+// is DYPOOL, stays on the tensor-core path).
+// Measured (profiles/r1_bench_smallk.json): correct (68/68 GPU tests) but no faster -- forward 60 vs 56 us, weight
+// gradient 102 vs 113 us once the split reduction is parallel; every lane re-evaluating the gather context (index,
+// coordinates, three divisions) per row costs what the tensor-core tile wastes.  Opt-in with PN2_SMALLK=1.
 #include <stdlib.h>
 
 #include "mlp_rows.cuh"
@@ -146,7 +149,7 @@ smallk_wgrad_kernel(const __grid_constant__ GemmArgs g) {
 bool smallk_on() {
   static const bool on = [] {
     const char *e = getenv("PN2_SMALLK");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';  // opt-in, see the header comment
   }();
   return on;
 }
