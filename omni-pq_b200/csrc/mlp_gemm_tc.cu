@@ -18,6 +18,8 @@
 //     stored with 128-byte row segments; BatchNorm partial column sums by a warp butterfly transpose-reduce.
 // The operands are produced by threads rather than TMA because every A element needs an element-wise
 // transform (that fusion is the point of the kernel); the weights are small and L2 resident.
+#include <atomic>
+
 #include "mlp_rows.cuh"
 #include "pn2_sm100.cuh"
 
@@ -1021,14 +1023,14 @@ int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
   // one counter slot per launch in flight (a captured graph keeps replaying the slot it was captured with)
   static thread_local int *counters = nullptr;
   static thread_local int counters_dev = -1;
-  static thread_local unsigned next_slot = 0;
+  static std::atomic<unsigned> next_slot{0};  // process-wide: launches from different threads / streams never share a slot
   if (counters_dev != dev) {
     void *p = nullptr;
     if (cudaGetSymbolAddress(&p, g_tile_counters) != cudaSuccess) return check_launch("gemm_tc_pbulk_kernel(counters)");
     counters = static_cast<int *>(p);
     counters_dev = dev;
   }
-  a.tile_counter = counters + (next_slot++ & 1023u);
+  a.tile_counter = counters + (next_slot.fetch_add(1, std::memory_order_relaxed) & 1023u);
   pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), PB_SMEM, stream, a);
   return check_launch("gemm_tc_pbulk_kernel");
 }
