@@ -116,3 +116,31 @@ def test_prefix_order_check_passes_only_when_the_answer_is_the_identity(name, em
             passed += ok
     if name in ("c1_uniform", "c2_scannet"):
         assert passed >= 2  # the ordered levels of an ordinary cloud take the shortcut
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_multipick_and_prefix_check_on_random_tie_heavy_clouds(seed, emul):
+    """Randomised adversarial inputs: points on a coarse integer lattice (massive exact distance ties), random
+    duplicates, a few points inside the skip radius, ragged sizes that change the reference block size -- the
+    multi-pick scheme must reproduce the oracle's order for every cluster size, and the prefix-order check must
+    pass exactly when the oracle's answer on the FPS-ordered cloud is the identity."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    n = int(rng.integers(40, 700))
+    m = int(rng.integers(2, n))
+    pts = rng.integers(0, 6, size=(n, 3)).astype(np.float32) * np.float32(0.25) + np.float32(0.125)
+    dup = rng.random(n) < 0.2
+    pts[dup] = pts[rng.integers(0, n, size=int(dup.sum()))]
+    near = rng.random(n) < 0.03
+    pts[near] = (rng.random((int(near.sum()), 3)) * 0.02).astype(np.float32)
+    xyz = torch.from_numpy(pts)[None].contiguous()
+    want = O.furthest_point_sample(xyz, m).numpy()[0]
+    for cs in (1, 2, 8):
+        got, _ = emul(pts, m, cs)
+        assert np.array_equal(got, want), (seed, n, m, cs, int(np.argmax(got != want)))
+    ordered = torch.gather(xyz, 1, torch.from_numpy(want).long()[None, :, None].expand(-1, -1, 3)).contiguous()
+    for cloud, mm in ((xyz, m), (ordered, max(2, m // 2)), (ordered, m - 1 if m > 2 else 2)):
+        if mm >= cloud.shape[1]:
+            continue
+        ref = O.furthest_point_sample(cloud, mm).numpy()[0]
+        identity = np.array_equal(ref, np.arange(mm, dtype=ref.dtype))
+        assert (emul.verify(cloud[0].numpy(), mm) == 0) == identity, (seed, n, mm, identity)
