@@ -157,10 +157,13 @@ int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *wt, const fl
 int pn2_mlp_tiles(int rows, int np); /* row tiles pn2_mlp_forward / pn2_mlp_dgrad use for this shape */
 
 /* BatchNorm statistics -> folded scale/shift (+ saved mean / invstd, running-stat update).
- * training != 0: batch statistics from `stats` (tiles partials) or, if sums != NULL, from the fp64 totals
- * sums[2][c] with `count` rows (SyncBatchNorm: totals all-reduced by the caller).  training == 0: running
- * statistics.  gamma/beta may be NULL (affine=False).  momentum < 0 means cumulative average. */
-int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream);
+ * training != 0: batch statistics from `stats` (tiles partials, `count` rows) or, if sums != NULL, from the fp64
+ * totals sums[2*c + 1] = (sum[c], sum of squares[c], row count) -- SyncBatchNorm (torch/nn/modules/_functions.py
+ * SyncBatchNorm.forward; enabled by the reference at models/pq_transformer.py:194): pn2_bn_reduce_stats writes
+ * this rank's totals and row count, the caller all-reduces the 2c+1 doubles, and the row count is consumed ON THE
+ * DEVICE (no host synchronisation).  training == 0: running statistics.  gamma/beta may be NULL (affine=False).
+ * momentum < 0 means cumulative average. */
+int pn2_bn_reduce_stats(int tiles, int c, int np, double count, const float *stats, double *sums, void *stream);
 int pn2_bn_finalize(int training, int tiles, int c, int np, double count, const float *stats, const double *sums,
                     const float *gamma, const float *beta, float *running_mean, float *running_var,
                     long long *num_batches_tracked, float momentum, float eps, float *scale, float *shift,
@@ -182,10 +185,13 @@ int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz, const flo
 int pn2_pool_bwd_tiles(int groups);
 
 /* BatchNorm backward coefficients: dy = ca*dz + cb + cc*y, dgamma, dbeta (training: batch statistics;
- * eval: ca = gamma*invstd, cb = cc = 0).  Input: partial sums (sum dz, sum dz*y) or fp64 totals. */
+ * eval: ca = gamma*invstd, cb = cc = 0).  Input: this rank's partial sums (sum dz, sum dz*y) in `stats`.
+ * SyncBatchNorm: `sums` = the totals over all ranks (2c doubles, all-reduced by the caller) and `count_dev` = the
+ * global row count on the device (element 2c of the forward's sums); they determine ca/cb/cc, while dgamma/dbeta
+ * are computed from the LOCAL partial sums like torch's SyncBatchNorm does (DDP averages them afterwards). */
 int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, const float *stats, const double *sums,
-                        const float *gamma, const float *mean, const float *invstd, float *ca, float *cb, float *cc,
-                        float *dgamma, float *dbeta, void *stream);
+                        const double *count_dev, const float *gamma, const float *mean, const float *invstd, float *ca,
+                        float *cb, float *cc, float *dgamma, float *dbeta, void *stream);
 
 /* dX = dY . W with dY given by `dy` (kind DY / DYPOOL); wp [np of forward][ldw] (FFMA kernel) and
  * wt [kp][np of forward] (tcgen05 kernel, may be NULL) are the prepared copies of W.  Modes:

@@ -338,14 +338,14 @@ _d = ctypes.c_double
 _prep = _sig("pn2_mlp_prep_weights", _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
 _mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _vp, _i, _vp, _ip_, _vp)
 _mlp_tiles = _sig("pn2_mlp_tiles", _i, _i, kernel=False)
-_bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _vp, _vp, _vp)
+_bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _d, _vp, _vp, _vp)
 _bn_fin = _sig("pn2_bn_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp)
 _pool = _sig("pn2_bn_relu_pool", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
 _to_pm = _sig("pn2_to_point_major", _i, _i, _i, _i, _i, _vp, _vp, _vp)
 _to_cm = _sig("pn2_to_channel_major", _i, _i, _i, _i, _vp, _vp, _vp)
 _pool_prep = _sig("pn2_pool_bwd_prep", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip_, _vp)
 _pool_tiles = _sig("pn2_pool_bwd_tiles", _i, kernel=False)
-_bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_bn_bwd = _sig("pn2_bn_bwd_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _dgrad = _sig("pn2_mlp_dgrad", _i, _rp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _ip_, _rp, _vp, _i, _vp, _vp, _vp)
 _wgrad = _sig("pn2_mlp_wgrad", _rp, _rp, _i, _i, _i, _i, _vp, _vp, _vp)
 lib.pn2_mlp_weight_floats.argtypes = [_i, _i]
@@ -389,9 +389,12 @@ def mlp_forward(rows, kp, np_, wt, wp=None, want_stats=True):
     return y, stats, tiles
 
 
-def bn_reduce_stats(stats, tiles, c, np_):
-    sums = torch.empty(2, c, dtype=torch.float64, device=stats.device)
-    _check(_bn_reduce(tiles, c, np_, _ptr(stats), _ptr(sums), _stream()))
+def bn_reduce_stats(stats, tiles, c, np_, count):
+    """Per-tile fp32 partials -> this rank's fp64 totals [2c+1] = (sums[c], second sums[c], `count` rows): the
+    buffer a SyncBatchNorm exchange all-reduces in one piece (the row count travels with the totals and is consumed
+    on the device, so the exchange needs no host synchronisation)."""
+    sums = torch.empty(2 * c + 1, dtype=torch.float64, device=stats.device)
+    _check(_bn_reduce(tiles, c, np_, float(count), _ptr(stats), _ptr(sums), _stream()))
     _launched()
     return sums
 
@@ -453,15 +456,19 @@ def pool_bwd_prep(gz, out_pm, arg, y, groups, group, c, ld):
     return stats, tiles
 
 
-def bn_bwd_finalize(training, tiles, c, np_, count, stats, sums, gamma, mean, invstd):
-    """-> (ca, cb, cc [np_] coefficient vectors, dgamma [c], dbeta [c])."""
+def bn_bwd_finalize(training, tiles, c, np_, count, stats, sums, gamma, mean, invstd, count_dev=None,
+                    dgamma_out=None, dbeta_out=None):
+    """-> (ca, cb, cc [np_] coefficient vectors, dgamma [c], dbeta [c]).  `sums` / `count_dev`: SyncBatchNorm totals
+    over all ranks and the global row count on the device; dgamma / dbeta always come from the local `stats`."""
     dev = mean.device
     co = _f32(dev, 3, np_)
-    dg = _f32(dev, 2, c)
-    _check(_bn_bwd(int(training), tiles, c, np_, float(count), _p(stats), _p(sums), _p(gamma), _ptr(mean), _ptr(invstd),
-                   _ptr(co[0]), _ptr(co[1]), _ptr(co[2]), _ptr(dg[0]), _ptr(dg[1]), _stream()))
+    if dgamma_out is None or dbeta_out is None:
+        dg = _f32(dev, 2, c)
+        dgamma_out, dbeta_out = dg[0], dg[1]
+    _check(_bn_bwd(int(training), tiles, c, np_, float(count), _p(stats), _p(sums), _p(count_dev), _p(gamma), _ptr(mean), _ptr(invstd),
+                   _ptr(co[0]), _ptr(co[1]), _ptr(co[2]), _ptr(dgamma_out), _ptr(dbeta_out), _stream()))
     _launched()
-    return co[0], co[1], co[2], dg[0], dg[1]
+    return co[0], co[1], co[2], dgamma_out, dbeta_out
 
 
 def mlp_dgrad_mask(dy, ncols, wp, prev_y, prev_scale, prev_shift, wt=None):
@@ -496,9 +503,10 @@ def mlp_dgrad_scatter(dy, ncols, wp, gather, dfeat, dxyz, centre_src, wt=None):
     _launched()
 
 
-def mlp_wgrad(dy, a, cout, cin, xyz_first, feat_pad, dev):
+def mlp_wgrad(dy, a, cout, cin, xyz_first, feat_pad, dev, out=None):
+    """-> dW (cout, cin); written into `out` (any tensor of cout*cin contiguous floats) when given."""
     ws = _f32(dev, max(1, lib.pn2_mlp_wgrad_workspace(dy.rows, dy.cols, a.cols)))
-    dw = _f32(dev, cout, cin)
+    dw = _f32(dev, cout, cin) if out is None else out
     _annotate(f"gemm_kernel<wgrad>[{dy.rows}:{dy.cols}x{a.cols}]", flops=2.0 * dy.rows * dy.cols * a.cols, nbytes=4.0 * dy.rows * (2 * dy.cols + a.cols))
     _check(_wgrad(ctypes.byref(dy), ctypes.byref(a), cout, cin, int(xyz_first), feat_pad, _ptr(ws), _ptr(dw), _stream()))
     _launched(2)

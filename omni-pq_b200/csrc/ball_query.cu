@@ -97,6 +97,41 @@ ball_query_kernel(int n, int m, float radius, int nsample, const float *__restri
   }
 }
 
+// Any nsample (the staged kernel above keeps 8 x 8 x nsample indices in shared memory and is used up to
+// kBqMaxSample): one warp per centre scans the whole cloud 32 points per step and appends the in-ball lanes straight
+// to the output row in index order (ballot + prefix popcount), then pads with the first hit.  Same results as the
+// reference's sequential scan (ball_query_gpu.cu:27-46), which accepts every nsample.
+__global__ void __launch_bounds__(256)
+ball_query_warp_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz,
+                       const float *__restrict__ xyz, int *__restrict__ idx) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int batch = blockIdx.y;
+  if (j >= m) return;
+  xyz += static_cast<size_t>(batch) * n * 3;
+  new_xyz += (static_cast<size_t>(batch) * m + j) * 3;
+  int *row = idx + (static_cast<size_t>(batch) * m + j) * nsample;
+  const float radius2 = __fmul_rn(radius, radius);
+  const float cx = __ldg(new_xyz + 0), cy = __ldg(new_xyz + 1), cz = __ldg(new_xyz + 2);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int cnt = 0, first = 0;
+  for (int t = 0; t < n && cnt < nsample; t += 32) {
+    const int k = t + lane;
+    const bool in_range = k < n;
+    const int kk = in_range ? k : 0;
+    const float d2 = dist2(cx, cy, cz, __ldg(xyz + kk * 3 + 0), __ldg(xyz + kk * 3 + 1), __ldg(xyz + kk * 3 + 2));
+    const bool hit = in_range && d2 < radius2;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (bal == 0u) continue;
+    if (cnt == 0) first = t + __ffs(bal) - 1;
+    const int pos = cnt + __popc(bal & lt_mask);
+    if (hit && pos < nsample) row[pos] = k;
+    cnt = min(nsample, cnt + __popc(bal));
+  }
+  for (int s = cnt + lane; s < nsample; s += 32) row[s] = first;  // empty ball: first == 0 (zero-filled in the reference)
+}
+
 }  // namespace
 }  // namespace pn2
 
@@ -105,13 +140,15 @@ PN2_EXPORT int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   using namespace pn2;
   PN2_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample > 0, "pn2_ball_query: bad extents b=%d n=%d m=%d nsample=%d", b, n, m,
               nsample);
-  if (nsample > kBqMaxSample) {
-    set_error("pn2_ball_query: nsample=%d exceeds the supported maximum %d", nsample, kBqMaxSample);
-    return PN2_ERR_UNSUPPORTED;
-  }
   if (b == 0 || m == 0) return PN2_OK;
   PN2_REQUIRE(new_xyz && xyz && idx, "pn2_ball_query: null pointer");
   PN2_REQUIRE(b <= 65535, "pn2_ball_query: b=%d exceeds the grid limit", b);
+  if (nsample > kBqMaxSample) {  // staging buffer would exceed 32 KB: warp-per-centre kernel, any nsample
+    dim3 wgrid((m + 7) / 8, b);
+    pn2::launch(ball_query_warp_kernel, dim3(wgrid), dim3(256), 0, static_cast<cudaStream_t>(stream), n, m, radius, nsample, new_xyz,
+                xyz, idx);
+    return check_launch("pn2_ball_query(warp)");
+  }
   dim3 grid((m + kBqCentres - 1) / kBqCentres, b);
   const size_t smem = sizeof(int) * kBqCentres * kBqWarps * static_cast<size_t>(nsample);  // <= 32 KB
   pn2::launch(ball_query_kernel, dim3(grid), dim3(kBqWarps * 32), smem, static_cast<cudaStream_t>(stream), n, m, radius, nsample, new_xyz, xyz,

@@ -14,6 +14,7 @@ namespace pn2 {
 namespace {
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float relu_nan(float v) { return !(v <= 0.f) ? v : 0.f; }  // NaN-propagating ReLU
 
 // ---- (B,C,N) <-> (B,N,ld) ----------------------------------------------------------------------------
 // 32x32 tiles through shared memory, coalesced on both sides; columns c..ld-1 of the point-major side
@@ -103,11 +104,13 @@ __device__ __forceinline__ void total_of(const float *stats, int tiles, int np, 
 }
 
 __global__ void __launch_bounds__(kStatCh * kStatLanes)
-bn_reduce_stats_kernel(int tiles, int c, int np, const float *__restrict__ stats, double *__restrict__ sums) {
+bn_reduce_stats_kernel(int tiles, int c, int np, double count, const float *__restrict__ stats,
+                       double *__restrict__ sums) {
   pdl_prologue();
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
   double s1, s2;
   total_of(stats, tiles, np, ch, ch < c, s1, s2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * c] = count;  // rows behind these totals: reduced with them
   if (threadIdx.x / kStatCh != 0 || ch >= c) return;
   sums[ch] = s1;
   sums[c + ch] = s2;
@@ -134,7 +137,7 @@ __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, doubl
   }
   float mean, invstd;
   if (training) {
-    if (sums) { s1 = sums[ch]; s2 = sums[c + ch]; }
+    if (sums) { s1 = sums[ch]; s2 = sums[c + ch]; count = sums[2 * c]; }  // all-reduced totals carry the global row count
     const double mu = s1 / count;
     double var = s2 / count - mu * mu;  // biased variance (what BatchNorm normalises with)
     if (var < 0.0) var = 0.0;
@@ -165,24 +168,30 @@ __global__ void bn_bump_counter_kernel(long long *nbt) {
 
 __global__ void bn_bwd_finalize_kernel(int training, int tiles, int c, int np, double count,
                                        const float *__restrict__ stats, const double *__restrict__ sums,
-                                       const float *__restrict__ gamma, const float *__restrict__ mean,
-                                       const float *__restrict__ invstd, float *__restrict__ ca,
-                                       float *__restrict__ cb, float *__restrict__ cc, float *__restrict__ dgamma,
-                                       float *__restrict__ dbeta) {
+                                       const double *__restrict__ count_dev, const float *__restrict__ gamma,
+                                       const float *__restrict__ mean, const float *__restrict__ invstd,
+                                       float *__restrict__ ca, float *__restrict__ cb, float *__restrict__ cc,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta) {
   pdl_prologue();
   const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
-  double s_dz = 0.0, s_dzy = 0.0;
-  if (!sums) total_of(stats, tiles, np, ch, ch < c, s_dz, s_dzy);  // block-cooperative: before any return
+  // this rank's totals of (dz, dz*y).  SyncBatchNorm: `sums` holds the totals over ALL ranks; they enter the
+  // input-gradient coefficients only -- dgamma / dbeta stay rank-local exactly like torch's SyncBatchNorm
+  // (batch_norm_backward_reduce returns local grad_weight / grad_bias; DDP averages them afterwards).
+  double l_dz = 0.0, l_dzy = 0.0;
+  if (stats) total_of(stats, tiles, np, ch, ch < c, l_dz, l_dzy);  // block-cooperative: before any return
   if (threadIdx.x / kStatCh != 0 || ch >= np) return;
   if (ch >= c) {
     ca[ch] = 0.f; cb[ch] = 0.f; cc[ch] = 0.f;
     return;
   }
+  if (count_dev) count = *count_dev;
+  double s_dz = l_dz, s_dzy = l_dzy;
   if (sums) { s_dz = sums[ch]; s_dzy = sums[c + ch]; }
+  if (!stats) { l_dz = s_dz; l_dzy = s_dzy; }
   const double mu = mean[ch], r = invstd[ch], gmm = gamma ? gamma[ch] : 1.0;
-  const double s_dzn = r * (s_dzy - mu * s_dz);  // sum dz * normalised y
-  if (dgamma) dgamma[ch] = static_cast<float>(s_dzn);
-  if (dbeta) dbeta[ch] = static_cast<float>(s_dz);
+  const double s_dzn = r * (s_dzy - mu * s_dz);  // sum dz * normalised y (over every rank's rows)
+  if (dgamma) dgamma[ch] = static_cast<float>(r * (l_dzy - mu * l_dz));
+  if (dbeta) dbeta[ch] = static_cast<float>(l_dz);
   const double s = gmm * r;
   if (training) {
     const double m1 = s_dz / count, m2 = s_dzn / count;
@@ -213,12 +222,13 @@ bn_relu_pool_kernel(int groups, int group, int ld, const float *__restrict__ y, 
   uchar4 bi = make_uchar4(0, 0, 0, 0);
   for (int s = 0; s < group; ++s) {
     const float4 v = ldg4(row + static_cast<size_t>(s) * ld);
-    const float a = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), b = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-    const float c = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), d = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-    if (a > best.x) { best.x = a; bi.x = s; }
-    if (b > best.y) { best.y = b; bi.y = s; }
-    if (c > best.z) { best.z = c; bi.z = s; }
-    if (d > best.w) { best.w = d; bi.w = s; }
+    // ReLU and max both propagate NaN like torch.relu / F.max_pool2d (a diverged run must not be masked)
+    const float a = relu_nan(fmaf(v.x, sc.x, sh.x)), b = relu_nan(fmaf(v.y, sc.y, sh.y));
+    const float c = relu_nan(fmaf(v.z, sc.z, sh.z)), d = relu_nan(fmaf(v.w, sc.w, sh.w));
+    if (a > best.x || a != a) { best.x = a; bi.x = s; }
+    if (b > best.y || b != b) { best.y = b; bi.y = s; }
+    if (c > best.z || c != c) { best.z = c; bi.z = s; }
+    if (d > best.w || d != d) { best.w = d; bi.w = s; }
   }
   *reinterpret_cast<float4 *>(out_pm + static_cast<size_t>(g) * ld + c4) = best;
   if (arg) *reinterpret_cast<uchar4 *>(arg + static_cast<size_t>(g) * ld + c4) = bi;
@@ -396,9 +406,10 @@ PN2_EXPORT int pn2_to_channel_major(int b, int c, int n, int stride, const float
   return transpose_launch(false, b, c, n, c, stride, src, dst, stream, "pn2_to_channel_major");
 }
 
-PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, const float *stats, double *sums, void *stream) {
+PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, double count, const float *stats, double *sums,
+                                   void *stream) {
   PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
-  pn2::launch(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, stats, sums);
+  pn2::launch(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, count, stats, sums);
   return check_launch("pn2_bn_reduce_stats");
 }
 
@@ -407,7 +418,7 @@ PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double co
                                float *running_var, long long *num_batches_tracked, float momentum, float eps,
                                float *scale, float *shift, float *mean, float *invstd, void *stream_) {
   PN2_REQUIRE(c > 0 && np >= c && (np % 4) == 0 && scale && shift && mean && invstd, "pn2_bn_finalize: bad arguments");
-  PN2_REQUIRE(training ? ((stats || sums) && count > 0.0) : (running_mean && running_var),
+  PN2_REQUIRE(training ? ((stats && count > 0.0) || sums) : (running_mean && running_var),
               "pn2_bn_finalize: %s", training ? "training needs statistics and a positive count" : "eval needs running statistics");
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   pn2::launch(bn_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, s, training, tiles, c, np, count, stats, sums, gamma, beta,
@@ -447,12 +458,13 @@ PN2_EXPORT int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz
 }
 
 PN2_EXPORT int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, double count, const float *stats,
-                                   const double *sums, const float *gamma, const float *mean, const float *invstd,
-                                   float *ca, float *cb, float *cc, float *dgamma, float *dbeta, void *stream) {
-  PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && count > 0.0,
+                                   const double *sums, const double *count_dev, const float *gamma, const float *mean,
+                                   const float *invstd, float *ca, float *cb, float *cc, float *dgamma, float *dbeta,
+                                   void *stream) {
+  PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && (count > 0.0 || count_dev),
               "pn2_bn_bwd_finalize: bad arguments");
   pn2::launch(bn_bwd_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), 
-      training, tiles, c, np, count, stats, sums, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
+      training, tiles, c, np, count, stats, sums, count_dev, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
   return check_launch("pn2_bn_bwd_finalize");
 }
 

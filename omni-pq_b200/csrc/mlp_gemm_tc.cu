@@ -81,8 +81,8 @@ __device__ __forceinline__ float4 apply_raw(const pn2_rows &s, const RowCtx &c, 
   const float4 k0 = *reinterpret_cast<const float4 *>(coef + ci);
   const float4 k1 = *reinterpret_cast<const float4 *>(coef + coef_ld + ci);
   if (KIND == PN2_ROWS_BNRELU)
-    return make_float4(fmaxf(fmaf(r.x.x, k0.x, k1.x), 0.f), fmaxf(fmaf(r.x.y, k0.y, k1.y), 0.f),
-                       fmaxf(fmaf(r.x.z, k0.z, k1.z), 0.f), fmaxf(fmaf(r.x.w, k0.w, k1.w), 0.f));
+    return make_float4(relu_nan(fmaf(r.x.x, k0.x, k1.x)), relu_nan(fmaf(r.x.y, k0.y, k1.y)),
+                       relu_nan(fmaf(r.x.z, k0.z, k1.z)), relu_nan(fmaf(r.x.w, k0.w, k1.w)));
   const float4 k2 = *reinterpret_cast<const float4 *>(coef + 2 * coef_ld + ci);
   float4 dz = r.d;
   if (KIND == PN2_ROWS_DYPOOL)

@@ -7,6 +7,8 @@ namespace {
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// ReLU that propagates NaN like torch.relu does (fmaxf(NaN, 0) would return 0 and mask a diverged run)
+__device__ __forceinline__ float relu_nan(float v) { return !(v <= 0.f) ? v : 0.f; }
 
 // ---- row sources ------------------------------------------------------------------------------------
 struct RowCtx {
@@ -53,8 +55,8 @@ __device__ __forceinline__ float4 load4(const pn2_rows &s, const RowCtx &c, int 
   if (KIND == PN2_ROWS_PLAIN) return ldg4(s.x + c.off + c4);
   if (KIND == PN2_ROWS_BNRELU) {
     const float4 v = ldg4(s.x + c.off + c4), a = ldg4(s.c0 + c4), b = ldg4(s.c1 + c4);
-    return make_float4(fmaxf(fmaf(v.x, a.x, b.x), 0.f), fmaxf(fmaf(v.y, a.y, b.y), 0.f),
-                       fmaxf(fmaf(v.z, a.z, b.z), 0.f), fmaxf(fmaf(v.w, a.w, b.w), 0.f));
+    return make_float4(relu_nan(fmaf(v.x, a.x, b.x)), relu_nan(fmaf(v.y, a.y, b.y)),
+                       relu_nan(fmaf(v.z, a.z, b.z)), relu_nan(fmaf(v.w, a.w, b.w)));
   }
   if (KIND == PN2_ROWS_GATHER) {
     if (c4 < s.feat_cols) return ldg4(s.x + c.off + c4);

@@ -121,36 +121,36 @@ def _sync_group(bn):
     return group if dist.get_world_size(group) > 1 else None
 
 
-def all_reduce_stats(sums, count, group):
-    """SyncBatchNorm exchange: `sums` = fp64 [2, C] per-rank totals (sum, sum of squares -- or, in the
-    backward, sum dz and sum dz*y), `count` = rows on this rank.  One all-reduce of 2C+1 doubles per
-    BatchNorm layer and direction (the reference's SyncBatchNorm issues an all_gather of 2C+1 floats in
-    the forward and an all_reduce of 2C in the backward).  Returns (sums, global count)."""
-    flat = torch.cat([sums.reshape(-1), torch.tensor([float(count)], dtype=torch.float64, device=sums.device)])
-    dist.all_reduce(flat, group=group)
-    return flat[:-1].view_as(sums), float(flat[-1].item())
+def all_reduce_stats(sums, group):
+    """SyncBatchNorm exchange: `sums` = this rank's fp64 totals [2C+1] = (sum[C], second sum[C], row count) -- in the
+    backward (sum dz[C], sum dz*y[C], unused).  ONE in-place all-reduce per BatchNorm layer and direction (torch's
+    SyncBatchNorm issues an all_gather of 2C+1 floats in the forward and an all_reduce of 2C in the backward,
+    SURVEY.md 2.5); the reduced row count stays on the device and is consumed by the finalize kernels, so there is no
+    host synchronisation and the exchange can be captured in a CUDA graph."""
+    dist.all_reduce(sums, group=group)
+    return sums
 
 
 class _Layer:
     """Per-layer forward state kept for the backward pass."""
     __slots__ = ("cout", "cin", "kp", "np", "xyz_first", "feat_pad", "wt", "wp", "y", "scale", "shift", "mean",
-                 "invstd", "training", "count", "group", "gamma")
+                 "invstd", "training", "count", "count_dev", "group", "gamma", "params")
 
 
 def _bn_forward(L, bn, stats, tiles, rows):
     """BatchNorm statistics of L.y -> folded scale/shift (running stats in eval mode)."""
     training = bn.training
-    L.training, L.group, L.gamma = training, None, bn.weight
-    count, sums = float(rows), None
+    L.training, L.group, L.gamma, L.count_dev = training, None, bn.weight, None
+    sums = None
     if training:
         pg = _sync_group(bn)
         if pg is not None:
-            sums, count = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np), rows, pg)
-            L.group = pg
-        if count <= 1:
+            sums = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np, rows), pg)
+            L.group, L.count_dev = pg, sums[2 * L.cout:]  # global row count, device resident
+        elif rows <= 1:
             raise ValueError("Expected more than 1 value per channel when training")
-    L.count = count
-    L.scale, L.shift, L.mean, L.invstd = K.bn_finalize(training, tiles, L.cout, L.np, count, stats, sums, bn)
+    L.count = float(rows)
+    L.scale, L.shift, L.mean, L.invstd = K.bn_finalize(training, tiles, L.cout, L.np, L.count, stats, sums, bn)
 
 
 def _prep_layers(layers, kp0, xyz_first, feat_pad):
@@ -160,6 +160,7 @@ def _prep_layers(layers, kp0, xyz_first, feat_pad):
     for li, (conv, bn) in enumerate(layers):
         L = _Layer()
         L.cout, L.cin = conv.weight.shape[0], conv.weight.shape[1]
+        L.params = (conv.weight, bn.weight, bn.bias)
         L.kp, L.np = kp, pad4(L.cout)
         L.xyz_first, L.feat_pad = (xyz_first, feat_pad) if li == 0 else (0, 0)
         L.wt, L.wp = K.mlp_prep_weights(conv.weight.detach().view(L.cout, L.cin), L.xyz_first, L.feat_pad, L.kp, L.np)
@@ -180,11 +181,22 @@ def _run_mlp(layers, state, rows0, nrows):
 
 
 def _bn_backward(L, stats, tiles):
-    """-> (ca, cb, cc, dgamma, dbeta) for dy = ca*dz + cb + cc*y."""
+    """-> (ca, cb, cc, dgamma, dbeta) for dy = ca*dz + cb + cc*y.  Under SyncBatchNorm the sums of (dz, dz*y) are
+    all-reduced for the input-gradient coefficients; dgamma / dbeta stay rank-local (DDP averages them), exactly
+    like torch.nn.SyncBatchNorm's backward."""
     sums = None
     if L.group is not None:
-        sums, _ = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np), 0, L.group)
-    return K.bn_bwd_finalize(L.training, tiles, L.cout, L.np, L.count, stats, sums, L.gamma.detach(), L.mean, L.invstd)
+        sums = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np, 0), L.group)
+    return K.bn_bwd_finalize(L.training, tiles, L.cout, L.np, L.count, stats, sums, L.gamma.detach(), L.mean, L.invstd,
+                             count_dev=L.count_dev, dgamma_out=_slot(L.params[1]), dbeta_out=_slot(L.params[2]))
+
+
+def _slot(param):
+    """Fresh view of the gradient-arena slice of `param` inside a graphed training step (graphed.py), else None.
+    A fresh view (not the arena's own tensor object) so that autograd's AccumulateGrad adopts it as param.grad
+    instead of cloning it."""
+    s = getattr(param, "_pn2_grad_slot", None)
+    return None if s is None else s.view(s.shape)
 
 
 def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
@@ -204,7 +216,7 @@ def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
             a_src = K.rows_bnrelu(P.y, nrows, P.np, P.np, P.scale, P.shift)
         else:
             a_src = rows0
-        dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device)
+        dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device, out=_slot(L.params[0]))
         grads[li] = (dw.view(L.cout, L.cin, 1, 1), dgamma, dbeta)
         if li > 0:
             dz, stats, tiles = K.mlp_dgrad_mask(dy, P.np, L.wp, P.y, P.scale, P.shift, wt=L.wt)
@@ -259,11 +271,10 @@ class _SAFunction(torch.autograd.Function):
                 ready = torch.cuda.Event()
                 ready.record(side)
             xyz.record_stream(side)
-            xyz_c.record_stream(side)
             feat_pm, ldf, state = activation_independent()
             main.wait_event(ready)
-            for t in (inds, new_xyz, idx):
-                t.record_stream(main)
+            for t in (xyz_c, inds, new_xyz, idx):  # allocated on (or, xyz_c, possibly aliasing memory of) the geometry
+                t.record_stream(main)              # stream's pool, read by GEMM 0 and the backward on this stream
         else:
             xyz_c, inds, new_xyz, idx = geometry()
             feat_pm, ldf, state = activation_independent()
@@ -286,6 +297,11 @@ class _SAFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_new_xyz, g_out, _g_inds, _g_pm):
+        with torch.cuda.device(ctx.saved_tensors[2].device):  # kernels launch on the current device's stream
+            return _SAFunction._backward(ctx, g_new_xyz, g_out)
+
+    @staticmethod
+    def _backward(ctx, g_new_xyz, g_out):
         state, rows0, nrows, arg, (b, n, m, ns, c_feat, ldf) = ctx.pn2
         _new_xyz, inds, out_pm = ctx.saved_tensors
         need_xyz, need_feat = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
@@ -320,8 +336,9 @@ class _SAFunction(torch.autograd.Function):
 def sa_forward(module, xyz, features, inds):
     layers = _mlp_layers(module.mlp_module)
     on_side = getattr(xyz, "_pn2_side", None) == (xyz._version, tuple(xyz.shape))
-    new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), on_side, xyz, features, inds,
-                                                   *_flat_params(layers))
+    with torch.cuda.device(xyz.device):  # the library launches on the CURRENT device's current stream
+        new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), on_side, xyz, features, inds,
+                                                       *_flat_params(layers))
     _remember_pm(out, out_pm)
     if _SIDE_STREAM:
         new_xyz._pn2_side = (new_xyz._version, tuple(new_xyz.shape))  # produced on the geometry stream
@@ -358,6 +375,11 @@ class _FPFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, _g_pm):
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            return _FPFunction._backward(ctx, g_out)
+
+    @staticmethod
+    def _backward(ctx, g_out):
         state, rows0, nrows, idx, weight, (b, n, m, c1, c2, ld1, ld2, ldx) = ctx.pn2
         (out_pm,) = ctx.saved_tensors
         need_unknow, need_known = ctx.needs_input_grad[5], ctx.needs_input_grad[6]
@@ -386,7 +408,8 @@ class _FPFunction(torch.autograd.Function):
 
 def fp_forward(module, unknown, known, unknow_feats, known_feats):
     layers = _mlp_layers(module.mlp)
-    out, out_pm = _FPFunction.apply(module, layers, _cached_pm(known_feats), unknown, known, unknow_feats, known_feats,
-                                    *_flat_params(layers))
+    with torch.cuda.device(unknown.device):
+        out, out_pm = _FPFunction.apply(module, layers, _cached_pm(known_feats), unknown, known, unknow_feats, known_feats,
+                                        *_flat_params(layers))
     _remember_pm(out, out_pm)
     return out

@@ -16,7 +16,7 @@
  *
  * Parity pinning: the reference ships no golden vectors for these ops, so
  * this oracle is pinned against the reference's own kernels compiled from /root/reference into
- * oracle/_ref (oracle/build_ref.py) and run on the B200 box (tests/test_gpu_ref_ext.py), and against
+ * oracle/_ref (oracle/build_ref.py) and run on the B200 box (tests/test_gpu_ops.py::test_index_ops_match_reference_kernels_live), and against
  * the frozen fixtures in tests/golden/ that both agree on.
  */
 #include <math.h>

@@ -17,7 +17,8 @@ Two layers:
    reference calls at pytorch_utils.py:88-95,43 and pointnet2_modules.py:255.
 
 Parity status: index paths are pinned against the reference's own CUDA kernels (oracle/_ref, run on
-the GPU box by tests/test_gpu_ref_ext.py) and the fixtures in tests/golden; the MLP arithmetic is
+the GPU box by tests/test_gpu_ops.py) and the fixtures in tests/golden; the Python glue restated here is
+pinned against the reference's own pointnet2/*.py by tests/test_ref_glue_cpu.py; the MLP arithmetic is
 "parity unpinned" in the reference (it has no test at that boundary) and is anchored on
 torch fp32.
 """
@@ -323,42 +324,9 @@ class OracleBackbone(nn.Module):  # models/backbone_module.py:33-139 (width=2, d
         return ep
 
 
-# ---- synthetic inputs, numpy PCG64 so every implementation sees identical bits ---
-def uniform_cloud(b, n, c_feat=3, seed=0):
-    """C1: xyz ~ U[0,1)^3, feats ~ N(0,1)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    xyz = rng.random((b, n, 3), dtype=np.float64).astype(np.float32)
-    feats = rng.standard_normal((b, c_feat, n)).astype(np.float32)
-    return torch.from_numpy(xyz), torch.from_numpy(feats)
+# ---- synthetic inputs: tools/synth_clouds.py (neutral module; re-exported for the tests' convenience) ----
+import sys as _sys
 
-
-def scannet_like_cloud(n=40000, seed=1234, c_feat=3, centred=False, yaw=False):
-    """C2/C5: points on the walls/floor/ceiling of an axis-aligned room plus 5-20 furniture boxes,
-    area-proportional sampling, 5 mm jitter, random point order.  Returns (n, 3+c_feat) float32."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    W, L, H = rng.uniform(3, 8), rng.uniform(3, 8), rng.uniform(2.4, 3.0)
-    boxes = [(0.0, 0.0, 0.0, W, L, H)]
-    for _ in range(int(rng.integers(5, 21))):
-        sx, sy, sz = rng.uniform(0.3, 2.0), rng.uniform(0.3, 2.0), rng.uniform(0.3, 1.5)
-        ox, oy = rng.uniform(0, max(W - sx, 0.1)), rng.uniform(0, max(L - sy, 0.1))
-        boxes.append((ox, oy, 0.0, sx, sy, sz))
-    faces = []  # (origin, u, v, area)
-    for (ox, oy, oz, sx, sy, sz) in boxes:
-        o = np.array([ox, oy, oz])
-        ex, ey, ez = np.array([sx, 0, 0]), np.array([0, sy, 0]), np.array([0, 0, sz])
-        for (p, u, v) in [(o, ex, ey), (o + ez, ex, ey), (o, ex, ez), (o + ey, ex, ez), (o, ey, ez), (o + ex, ey, ez)]:
-            faces.append((p, u, v, np.linalg.norm(np.cross(u, v))))
-    areas = np.array([f[3] for f in faces])
-    which = rng.choice(len(faces), size=n, p=areas / areas.sum())
-    uv = rng.random((n, 2))
-    P = np.stack([faces[w][0] + uv[i, 0] * faces[w][1] + uv[i, 1] * faces[w][2] for i, w in enumerate(which)])
-    P = P + rng.normal(0.0, 0.005, size=P.shape)
-    if centred:
-        P = P - np.array([W / 2, L / 2, 0.0])
-    if yaw:
-        a = rng.uniform(0, 2 * np.pi)
-        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
-        P = P @ R.T
-    P = P[rng.permutation(n)]
-    col = rng.uniform(-0.5, 0.5, size=(n, c_feat))
-    return torch.from_numpy(np.concatenate([P, col], axis=1).astype(np.float32))
+if os.path.dirname(_HERE) not in _sys.path:
+    _sys.path.insert(0, os.path.dirname(_HERE))
+from tools.synth_clouds import scannet_like_cloud, uniform_cloud  # noqa: E402,F401

@@ -8,7 +8,7 @@ The reference pins no known-answer vectors for this path, and its
 GPU.  So `pn2_golden_ref.npz` is generated ON THE B200 BOX from the unmodified reference kernels
 compiled by oracle/build_ref.py (written to gpurun_out/ there, then committed here), and
 `pn2_golden_oracle.npz` from the CPU oracle in the build container; tests/test_oracle_cpu.py checks the
-oracle against both, tests/test_gpu_parity.py checks the B200 kernels against both.
+oracle against both, tests/test_gpu_ops.py checks the B200 kernels against both.
 Each file stores, per case of tests/cases.py, every index tensor plus a digest of the input cloud.
 """
 import argparse

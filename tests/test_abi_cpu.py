@@ -50,7 +50,9 @@ def test_argument_errors_are_codes_not_exits(built_lib):
     rc = lib.pn2_furthest_point_sampling(1, 16, 4, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.pn2_last_error()
     assert lib.pn2_ball_query(1, 16, 4, ctypes.c_float(0.1), 0, None, None, None, None) == -1
-    assert lib.pn2_ball_query(1, 16, 4, ctypes.c_float(0.1), 100000, None, None, None, None) == -2
+    # every nsample is accepted like in the reference (ball_query_gpu.cu has no cap): only the null pointers are refused
+    assert lib.pn2_ball_query(1, 16, 4, ctypes.c_float(0.1), 100000, None, None, None, None) == -1
+    assert b"null" in lib.pn2_last_error()
     assert lib.pn2_three_nn(-1, 1, 1, None, None, None, None, None) == -1
     assert lib.pn2_group_points(1, 4, 16, 1 << 20, 1 << 20, None, None, None, None) == -1  # int32 overflow
     # empty problems are fine and touch nothing

@@ -1,6 +1,7 @@
-"""world_size-2 gloo tests (CPU) of the host-side multi-rank logic: the SyncBatchNorm statistics exchange
-used by the fused path, scene sharding of the benchmark harness, and DDP gradient averaging over the
-reference-named parameters."""
+"""world_size-2 gloo tests (CPU) of the repository's host-side multi-rank logic: the SyncBatchNorm statistics
+exchange of the fused path (fused.all_reduce_stats: one [2C+1] fp64 buffer, row count reduced with the sums) and
+bench.py's scene sharding / max-over-ranks timing helpers.  The kernels' side of SyncBatchNorm (device-side count,
+rank-local dgamma/dbeta) is covered on the GPU by tests/test_gpu_syncbn.py."""
 import os
 import sys
 
@@ -43,11 +44,14 @@ def _syncbn_stats(rank, world):
     rows = [300, 400]
     start = sum(rows[:rank])
     mine = full[start:start + rows[rank]]
-    sums = torch.stack([mine.sum(0), (mine * mine).sum(0)])
-    tot, count = fused.all_reduce_stats(sums, rows[rank], dist.group.WORLD)
-    mean = tot[0] / count
-    var = tot[1] / count - mean * mean
-    ok = count == 700.0 and torch.allclose(mean, full.mean(0)) and torch.allclose(var, full.var(0, unbiased=False))
+    # the layout pn2_bn_reduce_stats produces: (sum[C], sum of squares[C], rows of this rank)
+    sums = torch.cat([mine.sum(0), (mine * mine).sum(0), torch.tensor([float(rows[rank])], dtype=torch.float64)])
+    tot = fused.all_reduce_stats(sums, dist.group.WORLD)
+    assert tot.data_ptr() == sums.data_ptr()  # in place: no host round trip, no re-allocation
+    count = tot[24]
+    mean = tot[:12] / count
+    var = tot[12:24] / count - mean * mean
+    ok = float(count) == 700.0 and torch.allclose(mean, full.mean(0)) and torch.allclose(var, full.var(0, unbiased=False))
     return bool(ok)
 
 
@@ -56,36 +60,24 @@ def test_syncbn_statistics_exchange_gloo(built_lib):
     assert out == {0: True, 1: True}
 
 
-def _ddp_grad_average(rank, world):
-    """DDP over the reference-named SharedMLP parameters: gradients are averaged across ranks (what
-    train.py:382 relies on).  CPU tensors go through the module's op-level fallback only at the nn level."""
-    import pytorch_utils as P
-    torch.manual_seed(0)
-    mlp = P.SharedMLP([6, 8, 4], bn=True)
-    ddp = torch.nn.parallel.DistributedDataParallel(mlp, broadcast_buffers=False)
-    g = torch.Generator().manual_seed(rank)
-    x = torch.randn(2, 6, 5, 3, generator=g)
-    ddp(x).sum().backward()
-    w = mlp.layer0.conv.weight.grad.clone()
-    gathered = [torch.zeros_like(w) for _ in range(world)]
-    dist.all_gather(gathered, w)
-    return bool(torch.allclose(gathered[0], gathered[1]))
-
-
-def test_ddp_gradient_allreduce_gloo(built_lib):
-    out = _spawn(_ddp_grad_average)
-    assert out == {0: True, 1: True}
-
-
 def _bench_sharding(rank, world):
-    """bench.py gives every rank its own scenes (seed offset by rank) and reports max-over-ranks time."""
-    ms = torch.tensor([10.0 + rank], dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    seed0 = 1234 + 100 * rank
-    return (float(ms.item()), seed0)
+    """bench.py: every rank draws its own scenes (scene_seed) and the step time is the max over ranks."""
+    import bench
+    ms = bench.max_over_ranks(10.0 + rank, torch.device("cpu"), world)
+    return (ms, bench.scene_seed(rank))
 
 
 def test_bench_sharding_and_max_reduce_gloo(built_lib):
     out = _spawn(_bench_sharding)
     assert out[0][0] == out[1][0] == 11.0
     assert out[0][1] != out[1][1]
+
+
+def test_sync_group_detection(built_lib):
+    """fused._sync_group: plain BatchNorm, eval mode or no process group -> no exchange."""
+    import fused
+    bn = torch.nn.SyncBatchNorm(4)
+    assert fused._sync_group(bn) is None            # no process group initialised
+    assert fused._sync_group(torch.nn.BatchNorm2d(4)) is None
+    bn.eval()
+    assert fused._sync_group(bn) is None
