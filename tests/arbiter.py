@@ -1,0 +1,107 @@
+"""fp64 arbiter for the float paths (test infrastructure).
+
+Gradient tolerances must not be fitted to the observed error of one implementation.  Instead both fp32
+implementations -- ours (GPU) and the oracle (the reference's glue over torch CPU fp32) -- are measured against the
+SAME computation carried out in float64, and ours passes when its distance to fp64 is not larger than a small
+multiple of the fp32 oracle's own distance to fp64:
+
+        err(ours, fp64)  <=  FACTOR * err(oracle_fp32, fp64) + FLOOR
+
+The discrete decisions (FPS order, ball-query / 3-NN indices, and the 3-NN distances the weights are built from)
+are taken from the fp32 oracle kernels -- they are integer outputs that all three sides share bit for bit -- so
+the fp64 computation is the exact-arithmetic version of the SAME function: grouping by those indices, centre
+subtraction, /radius, concat, conv1x1 + training/eval BatchNorm + ReLU, max-pool, interpolation, in double.
+"""
+import copy
+
+import torch
+import torch.nn.functional as F
+
+FACTOR = 3.0    # ours runs the contraction as 3xTF32 (1e-6 vs fp64) where torch CPU runs fp32 FMA (3e-7): the
+                # forward perturbation -- and with it the number of ReLU / max-pool mask flips in the backward -- is up
+                # to ~3x the oracle's; anything beyond that is a defect, not rounding
+FLOOR = 2e-6
+
+
+def rel_l2(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def rel_max(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def _group(t, idx):
+    """t (B,C,N) double, idx (B,m,ns) -> (B,C,m,ns)."""
+    b, c, n = t.shape
+    _, m, ns = idx.shape
+    flat = idx.long().reshape(b, 1, m * ns).expand(b, c, m * ns)
+    return torch.gather(t, 2, flat).reshape(b, c, m, ns)
+
+
+def sa_forward64(mod64, O, xyz, features64, inds=None, xyz64=None):
+    """OracleSAModuleVotes.forward in float64 on the fp32 oracle's index decisions.  xyz: fp32 (B,N,3) coordinates the
+    kernels see; xyz64: the same values as a float64 tensor (pass one that requires grad to get the xyz gradient)."""
+    if inds is None:
+        inds = O.furthest_point_sample(xyz, mod64.npoint)
+    if xyz64 is None:
+        xyz64 = xyz.double()
+    new_xyz32 = torch.gather(xyz, 1, inds.long()[..., None].expand(-1, -1, 3)).contiguous()
+    idx = O.ball_query(mod64.radius, mod64.nsample, xyz, new_xyz32)
+    new_xyz64 = torch.gather(xyz64, 1, inds.long()[..., None].expand(-1, -1, 3))
+    g_xyz = _group(xyz64.transpose(1, 2), idx) - new_xyz64.transpose(1, 2).unsqueeze(-1)
+    if mod64.normalize_xyz:
+        g_xyz = g_xyz / mod64.radius
+    if features64 is not None:
+        g = torch.cat([g_xyz, _group(features64, idx)], dim=1) if mod64.use_xyz else _group(features64, idx)
+    else:
+        g = g_xyz
+    h = mod64.mlp_module(g)
+    h = F.max_pool2d(h, kernel_size=[1, h.size(3)]).squeeze(-1)
+    return new_xyz64, h, inds
+
+
+def fp_forward64(mod64, O, unknown, known, unknow_feats64, known_feats64):
+    """OracleFPModule.forward in float64 on the fp32 oracle's 3-NN indices and squared distances."""
+    d2, idx = O.ext.three_nn(unknown.contiguous(), known.contiguous())
+    dist = torch.sqrt(d2.double())
+    r = 1.0 / (dist + 1e-8)
+    w = r / r.sum(dim=2, keepdim=True)
+    b, c, m = known_feats64.shape
+    n = idx.shape[1]
+    flat = idx.long().reshape(b, 1, n * 3).expand(b, c, n * 3)
+    taps = torch.gather(known_feats64, 2, flat).reshape(b, c, n, 3)
+    interp = (taps * w.unsqueeze(1)).sum(-1)
+    x = torch.cat([interp, unknow_feats64], dim=1) if unknow_feats64 is not None else interp
+    return mod64.mlp(x.unsqueeze(-1)).squeeze(-1)
+
+
+def backbone_forward64(bb64, O, cloud):
+    """OracleBackbone.forward in float64 (cloud fp32 (B,N,3+C))."""
+    xyz = cloud[..., :3].contiguous()
+    feats = cloud[..., 3:].transpose(1, 2).contiguous().double()
+    ep = {}
+    cur_xyz = xyz
+    for i, sa in enumerate((bb64.sa1, bb64.sa2, bb64.sa3, bb64.sa4), start=1):
+        _, feats, inds = sa_forward64(sa, O, cur_xyz, feats)
+        cur_xyz = torch.gather(cur_xyz, 1, inds.long()[..., None].expand(-1, -1, 3)).contiguous()
+        ep[f"sa{i}_xyz"], ep[f"sa{i}_features"] = cur_xyz, feats
+    f = fp_forward64(bb64.fp1, O, ep["sa3_xyz"], ep["sa4_xyz"], ep["sa3_features"], ep["sa4_features"])
+    f = fp_forward64(bb64.fp2, O, ep["sa2_xyz"], ep["sa3_xyz"], ep["sa2_features"], f)
+    ep["fp2_features"] = f
+    return ep
+
+
+def to64(module):
+    """Deep copy of an oracle module in float64 (same parameters, same BatchNorm buffers)."""
+    return copy.deepcopy(module).double()
+
+
+def check(name, ours, oracle32, exact64, factor=FACTOR, floor=FLOOR, metric=rel_l2):
+    """ours / oracle32 / exact64: tensors of the same quantity.  Returns the two errors; raises if ours is out of bounds."""
+    e_ours, e_ref = metric(ours, exact64), metric(oracle32, exact64)
+    assert e_ours <= factor * e_ref + floor, (
+        f"{name}: |ours - fp64| = {e_ours:.3e} exceeds {factor} x |oracle_fp32 - fp64| = {e_ref:.3e} (+{floor:.0e})")
+    return e_ours, e_ref

@@ -2,8 +2,10 @@
 grouping / BatchNorm / ReLU / max-pool and the hand-written backward) against the CPU oracle modules
 (the reference's Python glue restated over torch CPU fp32 conv / batch_norm / max_pool2d).
 Index outputs bit-exact; float outputs within 1e-5 of the output's max magnitude (BASELINE.json
-north_star: "within 1e-5 relative for the float feature paths"); gradients within 1e-4 (the reference's
-own backward is atomics-ordered, and a CPU/GPU BatchNorm chain amplifies rounding)."""
+north_star: "within 1e-5 relative for the float feature paths"); gradients within 1e-4 in max-norm on the
+small shapes.  At sizes with millions of ReLU / max-pool kinks a max-norm bound on gradients is ill-posed
+(one flipped mask changes an element by O(1)); there the bound is not fitted to the observed error but
+ARBITRATED against float64 (tests/arbiter.py): |ours - fp64| <= 3 x |oracle_fp32 - fp64| + 2e-6 in relative L2."""
 import numpy as np
 import pytest
 import torch
@@ -26,6 +28,12 @@ def K(built_lib):
 def O():
     from oracle import pn2_oracle
     return pn2_oracle
+
+
+@pytest.fixture(scope="module")
+def A():
+    import arbiter
+    return arbiter
 
 
 def rel(a, b):
@@ -231,12 +239,14 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def grad_close(a, b, l2=5e-3):
-    """Gradient parity at sizes with millions of ReLU / max-pool kinks: relative L2.  A pre-activation within
-    rounding of zero flips its mask on one side only; through the training-mode BatchNorm backward (sums over
-    all rows) each flip also perturbs every other element at the 1e-5 level, so neither a max-norm nor an
-    outlier count is well posed here -- the small-shape tests hold gradients to 1e-4 in max-norm instead."""
-    return rel_l2(a, b) <= l2
+def _arbitrate_grads(A, tag, ours_named, oracle_named, exact_named):
+    """Every parameter gradient: |ours - fp64| <= FACTOR x |oracle_fp32 - fp64| + FLOOR (relative L2)."""
+    worst = (0.0, 0.0, None)
+    for (n1, p1), (_, p2), (_, p3) in zip(ours_named, oracle_named, exact_named):
+        e_ours, e_ref = A.check(f"{tag}: grad {n1}", p1.grad, p2.grad, p3.grad)
+        if e_ours > worst[0]:
+            worst = (e_ours, e_ref, n1)
+    return worst
 
 
 def _backbone_pair(O):
@@ -249,41 +259,43 @@ def _backbone_pair(O):
 
 
 @pytest.mark.parametrize("npts", [8192, 40000])
-def test_backbone_chain_matches_oracle(npts, K, O):
+def test_backbone_chain_matches_oracle(npts, K, O, A):
     """BASELINE.json configs[1]: ScanNet-shaped 40000 x 6 cloud through the full backbone, fwd+bwd.
 
-    Index outputs must be bit-exact through all four levels.  Float tolerances are looser than the
-    per-module 1e-5 because this is a CHAIN of 18 training-mode BatchNorm layers evaluated by two different
-    fp32 implementations (each module sees the other's slightly different output, not identical inputs):
-    the forward mismatch grows from 5e-7 (sa1) to ~1e-5 (fp2).  In the backward a mismatch of 1e-5 flips
-    the ReLU mask of the ~3e-5 fraction of pre-activations that lie within 1e-5 of zero (measured on this
-    input), each flip changing the gradient of one (position, channel) element by O(1) -- so gradients are
-    compared in relative L2 norm, and the max-norm outliers must stay confined to a small set of elements.
-    test_backbone_stages_identical_inputs below holds every module to 1e-5 on identical inputs."""
+    Index outputs must be bit-exact through all four levels.  Features: sa1 within 1e-5 of the oracle; the deeper
+    stages are a CHAIN of 18 training-mode BatchNorm layers in which each implementation feeds on its own slightly
+    different outputs (torch CPU fp32 itself is 4e-6 ... 6e-6 away from float64 at sa4 / fp2), so they and every
+    parameter gradient are arbitrated against the float64 evaluation of the same chain (tests/arbiter.py):
+    |ours - fp64| <= 3 x |oracle_fp32 - fp64| + 2e-6.  test_backbone_stages_identical_inputs holds every module to
+    1e-5 on identical inputs."""
     ours, oracle = _backbone_pair(O)
+    exact = A.to64(oracle)
     cloud = O.scannet_like_cloud(npts, seed=1234)[None]
     ep = ours(cloud.cuda())
     ep_o = oracle(cloud)
+    ep_x = A.backbone_forward64(exact, O, cloud)
     for k in ["sa1_inds", "sa2_inds", "fp2_inds"]:
         assert torch.equal(ep[k].cpu(), ep_o[k]), k
     for k in ["sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"]:
         assert torch.equal(ep[k].cpu(), ep_o[k]), k
-    for k in ["sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"]:
-        assert rel(ep[k], ep_o[k]) <= 5e-5, (k, rel(ep[k], ep_o[k]))
     assert rel(ep["sa1_features"], ep_o["sa1_features"]) <= FEAT_TOL
+    for k in ["sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"]:
+        A.check(k, ep[k], ep_o[k], ep_x[k], metric=A.rel_max)
     cot = torch.randn(ep_o["fp2_features"].shape, generator=torch.Generator().manual_seed(1))
     (ep["fp2_features"] * cot.cuda()).sum().backward()
     (ep_o["fp2_features"] * cot).sum().backward()
-    for (n1, p1), (_, p2) in zip(ours.named_parameters(), oracle.named_parameters()):
-        assert rel_l2(p1.grad, p2.grad) <= 2e-2, (n1, rel_l2(p1.grad, p2.grad))
+    (ep_x["fp2_features"] * cot.double()).sum().backward()
+    _arbitrate_grads(A, f"backbone[{npts}]", ours.named_parameters(), oracle.named_parameters(), exact.named_parameters())
     _check_bn_buffers(ours, oracle)
 
 
-def test_backbone_stages_identical_inputs(K, O):
+def test_backbone_stages_identical_inputs(K, O, A):
     """Every SA / FP module of the 40k-point backbone, fed the ORACLE's inputs for that stage (identical
-    inputs on both sides): indices bit-exact, features within 1e-5, gradients in relative L2 (max-norm is
-    ill-posed at 33M ReLU kinks per layer; the small-shape tests above hold gradients to 1e-4 in max-norm)."""
+    inputs on both sides): indices bit-exact, features within 1e-5 of the oracle, gradients arbitrated against
+    float64 (33M ReLU kinks per layer make a max-norm bound ill-posed; the small-shape tests above hold gradients to
+    1e-4 in max-norm)."""
     ours, oracle = _backbone_pair(O)
+    exact = A.to64(oracle)
     cloud = O.scannet_like_cloud(40000, seed=1234)[None]
     with torch.no_grad():
         ep_o = oracle(cloud)
@@ -292,37 +304,44 @@ def test_backbone_stages_identical_inputs(K, O):
     stages = [("sa1", xyz0, f0), ("sa2", ep_o["sa1_xyz"], ep_o["sa1_features"]),
               ("sa3", ep_o["sa2_xyz"], ep_o["sa2_features"]), ("sa4", ep_o["sa3_xyz"], ep_o["sa3_features"])]
     for name, xyz, feats in stages:
-        f_d, f_c = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True)
+        f_d, f_c, f_x = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True), feats.double().requires_grad_(True)
         nx, out, inds = getattr(ours, name)(xyz.cuda(), f_d)
         nx_o, out_o, inds_o = getattr(oracle, name)(xyz, f_c)
+        _, out_x, _ = A.sa_forward64(getattr(exact, name), O, xyz, f_x)
         assert torch.equal(inds.cpu(), inds_o) and torch.equal(nx.cpu(), nx_o), name
         assert rel(out, out_o) <= FEAT_TOL, (name, rel(out, out_o))
         cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(2))
         (out * cot.cuda()).sum().backward()
         (out_o * cot).sum().backward()
-        assert rel_l2(f_d.grad, f_c.grad) <= 5e-3, (name, rel_l2(f_d.grad, f_c.grad))
-        for (n1, p1), (_, p2) in zip(getattr(ours, name).named_parameters(), getattr(oracle, name).named_parameters()):
-            assert rel_l2(p1.grad, p2.grad) <= 5e-3, (name, n1, rel_l2(p1.grad, p2.grad))
+        (out_x * cot.double()).sum().backward()
+        A.check(f"{name}: d features", f_d.grad, f_c.grad, f_x.grad)
+        _arbitrate_grads(A, name, getattr(ours, name).named_parameters(), getattr(oracle, name).named_parameters(),
+                         getattr(exact, name).named_parameters())
     with torch.no_grad():
         fp1_o = oracle.fp1(ep_o["sa3_xyz"], ep_o["sa4_xyz"], ep_o["sa3_features"], ep_o["sa4_features"])
     for name, args in [("fp1", (ep_o["sa3_xyz"], ep_o["sa4_xyz"], ep_o["sa3_features"], ep_o["sa4_features"])),
                        ("fp2", (ep_o["sa2_xyz"], ep_o["sa3_xyz"], ep_o["sa2_features"], fp1_o))]:
         a_d = [t.cuda().requires_grad_(i >= 2) for i, t in enumerate(args)]
         a_c = [t.clone().requires_grad_(i >= 2) for i, t in enumerate(args)]
+        a_x = [t.double().requires_grad_(True) for t in args[2:]]
         out, out_o = getattr(ours, name)(*a_d), getattr(oracle, name)(*a_c)
+        out_x = A.fp_forward64(getattr(exact, name), O, args[0], args[1], a_x[0], a_x[1])
         assert rel(out, out_o) <= FEAT_TOL, (name, rel(out, out_o))
         cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(3))
         (out * cot.cuda()).sum().backward()
         (out_o * cot).sum().backward()
+        (out_x * cot.double()).sum().backward()
         for i in (2, 3):
-            assert rel_l2(a_d[i].grad, a_c[i].grad) <= 5e-3, (name, i)
-        for (n1, p1), (_, p2) in zip(getattr(ours, name).named_parameters(), getattr(oracle, name).named_parameters()):
-            assert rel_l2(p1.grad, p2.grad) <= 5e-3, (name, n1, rel_l2(p1.grad, p2.grad))
+            A.check(f"{name}: d input {i}", a_d[i].grad, a_c[i].grad, a_x[i - 2].grad)
+        _arbitrate_grads(A, name, getattr(ours, name).named_parameters(), getattr(oracle, name).named_parameters(),
+                         getattr(exact, name).named_parameters())
 
 
 def test_ffma_kernel_path_still_green():
     """The tcgen05 (3xTF32) GEMM is the default; PN2_TC=0 selects the fp32 FFMA kernel everywhere.  Re-run the
-    kernel-level and module-level checks of this file on that path in a fresh process."""
+    kernel-level and module-level checks of this file on that path in a fresh process (no retry: round 1's
+    intermittent failure of test_fp_matches_oracle[True] was hunted with tools/flake_hunt.py -- 900 in-process
+    repetitions on both paths, bit-identical results from run to run, profiles/r2_flake_hunt.txt)."""
     import os
     import subprocess
     import sys
@@ -330,26 +349,21 @@ def test_ffma_kernel_path_still_green():
     cmd = [sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k",
            "gemm or transposes or config1 or three_layer or without_features or fp_matches"]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
-    if r.returncode != 0:
-        # Open item: on this non-default path test_fp_matches_oracle[True] has failed
-        # intermittently (2 of ~20 runs, only as a child of a process that had run the whole suite; never
-        # reproduced directly, not an uninitialised read: PN2_DEBUG_POISON=1 is clean).  One retry keeps the
-        # debug path's check meaningful without making the suite flaky; both outputs are shown if it persists.
-        first = r.stdout[-1500:]
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
-        assert r.returncode == 0, first + "\n---- retry ----\n" + r.stdout[-3000:]
+    assert r.returncode == 0, r.stdout[-4000:]
 
 
-def test_config3_callers_vote_aggregation_and_fps_module_batch8(K, O):
+def test_config3_callers_vote_aggregation_and_fps_module_batch8(K, O, A):
     """BASELINE.json configs[2] exercises the path through the detector's callers: FPSModule
     (models/utils/pointnet_util.py:52-69 = furthest_point_sample + two gather_operations) and
     vote_aggregation = PointnetSAModuleVotes(256, 0.3, 16, [288+3,288,288,288]) (models/pq_transformer.py:159-166)
-    on a batch of 8 clouds of 1024 seeds, eval mode (BN running statistics), xyz carrying gradients."""
+    on a batch of 8 clouds of 1024 seeds, eval mode (BN running statistics) and train mode, xyz carrying gradients.
+    (The real pq_transformer.py / pointnet_util.py files run in tests/test_gpu_real_callers.py.)"""
     import pointnet2_modules as M
     import pointnet2_utils as U
     kw = dict(npoint=256, radius=0.3, nsample=16, use_xyz=True, normalize_xyz=True)
     ours, oracle = _pair(lambda: M.PointnetSAModuleVotes(mlp=[288, 288, 288, 288], **kw),
                          lambda: O.OracleSAModuleVotes(mlp=[288, 288, 288, 288], **kw), seed=3, randomise_bn=True)
+    exact = A.to64(oracle)
     xyz, feats = O.uniform_cloud(8, 1024, 288, seed=31)
     xyz = xyz * 0.9
     # FPSModule
@@ -361,27 +375,29 @@ def test_config3_callers_vote_aggregation_and_fps_module_batch8(K, O):
     assert torch.equal(g_xyz.cpu(), O.gather_operation(xyz.transpose(1, 2).contiguous(), inds_o))
     assert torch.equal(g_feat.cpu(), O.gather_operation(feats, inds_o))
     for train in (False, True):
-        ours.train(train)
-        oracle.train(train)
-        x_d, x_c = xyz.cuda().requires_grad_(True), xyz.clone().requires_grad_(True)
-        f_d, f_c = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True)
+        for m in (ours, oracle, exact):
+            m.train(train)
+        x_d, x_c, x_x = xyz.cuda().requires_grad_(True), xyz.clone().requires_grad_(True), xyz.double().requires_grad_(True)
+        f_d, f_c, f_x = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True), feats.double().requires_grad_(True)
         nx, out, ii = ours(x_d, f_d)
         nx_o, out_o, ii_o = oracle(x_c, f_c)
+        nx_x, out_x, _ = A.sa_forward64(exact, O, xyz, f_x, xyz64=x_x)
         assert torch.equal(ii.cpu(), ii_o) and torch.equal(nx.cpu(), nx_o)
         assert rel(out, out_o) <= (FEAT_TOL if not train else 2 * FEAT_TOL), (train, rel(out, out_o))
+        A.check("vote_aggregation out", out, out_o, out_x, metric=A.rel_max)
         cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(5))
         (out * cot.cuda()).sum().backward()
         (out_o * cot).sum().backward()
-        # 9.4M pre-activations per layer: relative L2 + confined outliers (see test_backbone_stages_identical_inputs)
-        assert grad_close(f_d.grad, f_c.grad), (train, rel_l2(f_d.grad, f_c.grad))
-        assert grad_close(x_d.grad, x_c.grad), (train, rel_l2(x_d.grad, x_c.grad))
-        for (n1, p1), (_, p2) in zip(ours.named_parameters(), oracle.named_parameters()):
-            assert rel_l2(p1.grad, p2.grad) <= 5e-3, (train, n1, rel_l2(p1.grad, p2.grad))
-        ours.zero_grad()
-        oracle.zero_grad()
+        (out_x * cot.double()).sum().backward()
+        A.check("d features", f_d.grad, f_c.grad, f_x.grad)
+        A.check("d xyz", x_d.grad, x_c.grad, x_x.grad)
+        _arbitrate_grads(A, f"vote_aggregation train={train}", ours.named_parameters(), oracle.named_parameters(),
+                         exact.named_parameters())
+        for m in (ours, oracle, exact):
+            m.zero_grad()
 
 
-def test_config5_arkit_fp_stress(K, O):
+def test_config5_arkit_fp_stress(K, O, A):
     """BASELINE.json configs[4]: ARKit-shaped 50000-point cloud (centred, yawed: points near the origin exercise
     the FPS skip), PointnetFPModule(mlp=[256+3,256,128]) from SA1's 2048 points to all 50000, fwd+bwd."""
     import pointnet2_modules as M
@@ -394,17 +410,109 @@ def test_config5_arkit_fp_stress(K, O):
     known = torch.gather(xyz, 1, inds_o.long()[..., None].expand(-1, -1, 3)).contiguous()
     kf = torch.randn(1, 256, 2048, generator=torch.Generator().manual_seed(8))
     ours, oracle = _pair(lambda: M.PointnetFPModule(mlp=[256 + 3, 256, 128]), lambda: O.OracleFPModule(mlp=[256 + 3, 256, 128]), seed=9)
-    ours.train()
-    oracle.train()
+    exact = A.to64(oracle)
+    for m in (ours, oracle, exact):
+        m.train()
     c_d, k_d = col.cuda().requires_grad_(True), kf.cuda().requires_grad_(True)
     c_c, k_c = col.clone().requires_grad_(True), kf.clone().requires_grad_(True)
+    c_x, k_x = col.double().requires_grad_(True), kf.double().requires_grad_(True)
     out = ours(xyz.cuda(), known.cuda(), c_d, k_d)
     out_o = oracle(xyz, known, c_c, k_c)
+    out_x = A.fp_forward64(exact, O, xyz, known, c_x, k_x)
     assert rel(out, out_o) <= FEAT_TOL, rel(out, out_o)
     cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(6))
     (out * cot.cuda()).sum().backward()
     (out_o * cot).sum().backward()
-    assert grad_close(c_d.grad, c_c.grad), rel_l2(c_d.grad, c_c.grad)
-    assert grad_close(k_d.grad, k_c.grad), rel_l2(k_d.grad, k_c.grad)
-    for (n1, p1), (_, p2) in zip(ours.named_parameters(), oracle.named_parameters()):
-        assert rel_l2(p1.grad, p2.grad) <= 5e-3, (n1, rel_l2(p1.grad, p2.grad))
+    (out_x * cot.double()).sum().backward()
+    A.check("d unknow_feats", c_d.grad, c_c.grad, c_x.grad)
+    A.check("d known_feats", k_d.grad, k_c.grad, k_x.grad)
+    _arbitrate_grads(A, "fp stress", ours.named_parameters(), oracle.named_parameters(), exact.named_parameters())
+
+
+# ---- fused three_nn: index path under ties ------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["lattice", "duplicates", "few_known"])
+def test_fused_fp_three_nn_indices_bit_exact_under_ties(case, K, O):
+    """fp_interpolate_kernel re-implements three_nn (interpolate_gpu.cu:14-64) inside the fused FP front end; its
+    index output must equal the reference kernel's on inputs FULL of exact distance ties: known points on an integer
+    lattice (many equidistant neighbours), duplicated known points (distance ties at every rank, ties -> lower index),
+    and m < 3 known points (unfilled slots keep index 0)."""
+    g = np.random.Generator(np.random.PCG64(17))
+    if case == "lattice":
+        known = torch.from_numpy(np.stack(np.meshgrid(*[np.arange(6)] * 3, indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32))
+        known = known[:, torch.from_numpy(g.permutation(known.shape[1]))].repeat(2, 1, 1).contiguous()
+        unknown = torch.from_numpy(g.integers(0, 11, (2, 700, 3)).astype(np.float32) * 0.5)   # lattice points and cell centres
+    elif case == "duplicates":
+        base = torch.from_numpy(g.random((2, 50, 3)).astype(np.float32))
+        known = torch.cat([base, base, base[:, :17]], dim=1).contiguous()
+        unknown = torch.cat([torch.from_numpy(g.random((2, 300, 3)).astype(np.float32)), base], dim=1).contiguous()
+    else:
+        known = torch.from_numpy(g.random((3, 2, 3)).astype(np.float32))
+        unknown = torch.from_numpy(g.random((3, 40, 3)).astype(np.float32))
+    b, n, m = unknown.shape[0], unknown.shape[1], known.shape[1]
+    c = 8
+    kf = torch.from_numpy(g.standard_normal((b, c, m)).astype(np.float32))
+    known_pm = K.to_point_major(kf.cuda())
+    x = torch.empty(b * n, c, device="cuda")
+    idx, w = K.fp_interpolate(unknown.cuda(), known.cuda(), known_pm, c, x, c)
+    d2_o, idx_o = O.ext.three_nn(unknown, known)
+    assert torch.equal(idx.cpu(), idx_o), case
+    if m >= 3:
+        w_o = O.fp_weights(torch.sqrt(d2_o))
+        assert torch.allclose(w.cpu(), w_o, rtol=1e-6, atol=1e-12), case
+        want = O.ext.three_interpolate(kf, idx_o, w_o).transpose(1, 2).reshape(b * n, c)
+        assert torch.allclose(x.cpu(), want, rtol=1e-5, atol=1e-6), case
+
+
+# ---- the timed path: whole-step CUDA graph == eager ----------------------------------------------------------------
+def test_graphed_train_step_matches_eager(K, O):
+    """bench.py times graphed.GraphedTrainStep replays (forward + backward + the side-stream fork/join in ONE CUDA
+    graph, gradients produced in the arena); every other parity test runs eagerly.  Over 4 replays with rotating
+    inputs the replay must reproduce the eager step: the forward output bit for bit (no atomics in the forward), every
+    gradient to 2e-6 of its max (the scatter-add backward kernels use fp32 atomics like the reference's, so the last
+    bits depend on the launch -- measured run-to-run spread of the eager path itself is the same size)."""
+    from backbone import Pointnet2Backbone
+    from graphed import GraphedTrainStep
+    torch.manual_seed(0)
+    model = Pointnet2Backbone(input_feature_dim=3).cuda().train()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = model
+
+        def forward(self, cloud):
+            return self.backbone(cloud)["fp2_features"]
+
+    net = Net()
+    scenes = torch.stack([O.scannet_like_cloud(20000, seed=77 + i) for i in range(3)]).cuda()
+    cot = torch.randn(1, 288, 1024, generator=torch.Generator().manual_seed(4)).cuda()
+    outs = {}
+
+    def loss_fn(out):
+        outs["last"] = out
+        return (out * cot).sum()
+
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    step = GraphedTrainStep(net, loss_fn, (scenes[0][None],))
+    static_out = outs["last"]
+    assert step.launches_per_step and step.launches_per_step > 50
+    params = [p for p in model.parameters()]
+    for it in range(4):
+        cloud = scenes[it % 3][None]
+        model.load_state_dict(state0)           # same BatchNorm running statistics on both sides
+        loss_g = step(cloud).clone()
+        out_g = static_out.clone()
+        grads_g = [p.grad.clone() for p in params]
+        bufs_g = {k: v.clone() for k, v in model.state_dict().items()}
+        model.load_state_dict(state0)
+        model.zero_grad(set_to_none=True)
+        out_e = net(cloud)
+        loss_e = (out_e * cot).sum()
+        loss_e.backward()
+        assert torch.equal(out_g, out_e), it
+        assert torch.equal(loss_g, loss_e.detach()), it
+        for (n, p), g in zip(model.named_parameters(), grads_g):
+            d = float((g - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-30))
+            assert d <= 2e-6, (it, n, d)
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, bufs_g[k]), (it, k)
