@@ -229,6 +229,10 @@ int pn2_fp_interpolate_grad(int b, int n, int m, int c, const float *dout, int l
  * GEMM kernels records [smid, t_start, t_prologue_done, t_mainloop_done, t_end, k_blocks] (globaltimer ns) for
  * tools/gemm_trace.py.  Pass NULL to switch it off (the default). */
 int pn2_debug_gemm_trace(unsigned long long *device_buf, int ctas);
+/* Same for the persistent async kernel, per tile: 8 x 8 uint64 per CTA = for each of a CTA's first 8 tiles
+ * [tile start, first k-block staged, last k-block staged, accumulator complete, epilogue done, MMA thread: first
+ * A stage seen, first weight stage seen, weight loader: first copy issued] (globaltimer ns). */
+int pn2_debug_gemm_trace2(unsigned long long *device_buf, int ctas);
 
 #ifdef __cplusplus
 }

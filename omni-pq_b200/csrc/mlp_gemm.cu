@@ -279,9 +279,11 @@ __device__ __forceinline__ void img_store(float *img, int cols, long long e, flo
   // e enumerates (tile, k-block, row-in-tile, col-in-block); returns through img the hi / lo placement
   const int c = static_cast<int>(e & 31), r = static_cast<int>((e >> 5) & 127);
   const long long stage = e >> 12;
-  uint32_t h;
+  uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  const float hi = __uint_as_float(h), lo = v - hi;
+  const float hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));  // rounded, not left to the tensor core's truncation
+  const float lo = __uint_as_float(l);
   const int off = (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));  // floats inside a 16 KB half
   float *st = img + stage * IMG_STAGE_FLOATS;
   st[off] = hi;
@@ -403,7 +405,7 @@ PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_p
   long long total = static_cast<long long>(kp) * np;
   if (img_t > total) total = img_t;
   if (img_p > total) total = img_p;
-  pn2::launch(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+  pn2::launch_small(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p);
   return check_launch("pn2_mlp_prep_weights");
 }
@@ -435,10 +437,6 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
     t.B = plain_rows(wp, np, kp, kp);
     t.b_img = wp + static_cast<size_t>(np) * kp;
     t.b_img_kblocks = (kp + 31) / 32;
-    if (smallk_eligible(a->kind, kp, np)) {
-      const int rc = smallk_forward_launch(&t, s);
-      if (rc != PN2_TC_UNSUPPORTED) return rc;
-    }
     const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
@@ -522,9 +520,7 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
 }
 
 PN2_EXPORT long long pn2_mlp_wgrad_workspace(int rows, int np, int kp) {
-  int splits = wgrad_splits(rows, np, kp);
-  if (smallk_eligible(PN2_ROWS_PLAIN, kp, np) && smallk_wgrad_splits(rows) > splits) splits = smallk_wgrad_splits(rows);
-  return static_cast<long long>(splits) * np * kp;
+  return static_cast<long long>(wgrad_splits(rows, np, kp)) * np * kp;
 }
 
 PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, int cin, int xyz_first, int feat_pad,
@@ -544,14 +540,6 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   g.k_per_split = ((rows + splits - 1) / splits + 31) / 32 * 32;  // multiple of both kernels' k-block
   g.out = ws; g.ldo = kp; g.out_split_stride = static_cast<long long>(np) * kp;
   int rc = PN2_TC_UNSUPPORTED;
-  if (rows > 0 && dy->kind == PN2_ROWS_DY && smallk_eligible(a->kind, kp, np)) {  // first layers: K <= 16
-    GemmArgs k = g;
-    const int ks = smallk_wgrad_splits(rows);
-    k.k_per_split = (rows + ks - 1) / ks;
-    rc = smallk_wgrad_launch(&k, ks, s);
-    if (rc != PN2_TC_UNSUPPORTED && rc != PN2_OK) return rc;
-    if (rc == PN2_OK) splits = ks;
-  }
   if (rows > 0 && rc == PN2_TC_UNSUPPORTED && gemm_tc_enabled()) {
     rc = gemm_tc_wgrad_launch(&g, splits, s);
     if (rc != PN2_TC_UNSUPPORTED && rc != PN2_OK) return rc;
@@ -576,10 +564,10 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   if (wide && nsl >= 64) {  // few, large slices (big outputs): the thread-per-element kernel is faster (measured)
     int nw = 1;
     while (nw < 16 && nw < nsl) nw *= 2;
-    pn2::launch(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,
+    pn2::launch_small(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,
                 ws, dw);
   } else {
-    pn2::launch(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl, ws, dw);
+    pn2::launch_small(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl, ws, dw);
   }
   return check_launch("pn2_mlp_wgrad(reduce)");
 }

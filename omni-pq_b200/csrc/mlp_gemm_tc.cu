@@ -115,6 +115,14 @@ __device__ __forceinline__ unsigned smid() {
   asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
   return r;
 }
+// per-tile timeline of the persistent async kernel (development aid, pn2_debug_gemm_trace2): 8 stamps for each of the
+// first 8 tiles of every CTA
+__device__ unsigned long long *g_trace2 = nullptr;
+__device__ int g_trace2_ctas = 0;
+__device__ __forceinline__ void tile_stamp(int ti, int k) {
+  if (g_trace2 != nullptr && ti < 8 && static_cast<int>(blockIdx.x) < g_trace2_ctas)
+    g_trace2[(static_cast<size_t>(blockIdx.x) * 8 + ti) * 8 + k] = globaltimer_ns();
+}
 // phase stamp of CTA `cta` (thread 0 only; no-op unless a trace buffer is installed)
 __device__ __forceinline__ void trace_stamp(const GemmArgs &g, int cta, int slot, unsigned long long v) {
   if (g.trace != nullptr && threadIdx.x == 0 && cta < g.trace_cap) g.trace[static_cast<size_t>(cta) * 6 + slot] = v;
@@ -391,35 +399,39 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   // issuing thread is not a producer: a thread that stages operands and issues MMAs holds its warp back
   // (a __syncthreads per k-block serialised staging and MMA issue: 1.3-1.9 us per k-block against 0.4 us of MMA
   // time, profiles/c3_gemm_trace.txt).
-  auto issue_mmas = [&](int kb) {
-    const int s = kb % TC_STAGES;
-    mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
-    tc_fence_after_sync();
-    const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
-    uint64_t a_hi, a_lo, b_hi, b_lo, step;
-    if (TRANS) {
-      a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
-      b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
-      b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
-      step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
-    } else {
-      a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
-      b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-      step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
-    }
-#pragma unroll
-    for (int ks = 0; ks < TK / 8; ++ks) {
-      const uint64_t adv = step * ks;
-      mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-      mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-      mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
-    }
-    mma_commit(&empty_bar[s]);
-    if (kb == num_kb - 1) mma_commit(done_bar);
-  };
   if (!producer) {
-    if (lane == 0)
-      for (int kb = 0; kb < num_kb; ++kb) issue_mmas(kb);
+    // MMA warp, CONVERGED: all 32 lanes run the loop on warp-uniform values and the MMAs / commits are issued under
+    // elect.sync, so the descriptors live in uniform registers (see elect_one() in pn2_sm100.cuh)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % TC_STAGES;
+      mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
+      tc_fence_after_sync();
+      const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
+      uint64_t a_hi, a_lo, b_hi, b_lo, step;
+      if (TRANS) {
+        a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
+        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
+        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
+        step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
+      } else {
+        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
+        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
+        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t adv = step * ks;
+          mma_tf32(tmem_u, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
+          mma_tf32(tmem_u, a_hi + adv, b_lo + adv, idesc, true);
+          mma_tf32(tmem_u, a_lo + adv, b_hi + adv, idesc, true);
+        }
+        mma_commit(&empty_bar[s]);
+        if (kb == num_kb - 1) mma_commit(done_bar);
+      }
+      __syncwarp();
+    }
   } else {
     // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
     // per warp and reclaimed when the MMAs that read it have completed
@@ -491,401 +503,191 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, cta_id, 5, static_cast<unsigned long long>(num_kb));
 }
 
-// ---- forward / data-gradient kernel with a bulk-copied weight operand ---------------------------------------
-// ncu of gemm_tc_kernel on the backbone's shapes (profiles/c1_ncu_gemm.json): the top stall is long_scoreboard
-// (global-load latency) at 16 resident warps -- one k-block of A and B in flight per thread is ~16 KB per SM,
-// far below what HBM needs.  For the non-transposed GEMMs B is the layer's weight matrix, identical for every
-// row tile, so its hi/lo split and 128-byte-swizzle layout are computed ONCE by pn2_mlp_prep_weights into an
-// image [n-tile][k-block][hi 16 KB | lo 16 KB]; here one thread fetches each 32 KB stage with a single
-// cp.async.bulk (complete_tx on a "full" mbarrier), two k-blocks ahead, into a 4-stage ring.  That removes half
-// of the staging instructions and the B registers, which pays for a second k-block of A prefetch per thread
-// (register sets: current, +1, +2, +3).  A: 2-stage ring written by all 16 warps as before.
-// Tiles are numbered with the n-tile fastest so that the CTAs sharing a row tile run together and the second
-// one reads A from L2.
-constexpr int BK_A_STAGES = 3, BK_B_STAGES = 3;
+// ---- forward / data-gradient kernels with a bulk-copied weight operand ---------------------------------------
+// For the non-transposed GEMMs B is the layer's weight matrix, identical for every row tile, so its hi/lo split and
+// 128-byte-swizzle layout are computed ONCE by pn2_mlp_prep_weights into an image [n-tile][k-block][hi 16 KB | lo 16 KB];
+// one thread fetches each 32 KB stage with a single cp.async.bulk (complete_tx on a "full" mbarrier).  Tiles are
+// numbered with the n-tile fastest so that the CTAs sharing a row tile run together and the second one reads A from L2.
 constexpr int BK_A_BYTES = 2 * TILE_BYTES, BK_B_BYTES = 2 * TILE_BYTES;  // hi + lo
-constexpr int BK_RING = BK_A_STAGES * BK_A_BYTES + BK_B_STAGES * BK_B_BYTES;
-constexpr int BK_SMEM = BK_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
 
-template <int AKIND, int EPI>
-__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
-gemm_tc_bulk_kernel(const __grid_constant__ GemmArgs g) {
-  pdl_prologue();
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char *ring_a = tiles, *ring_b = tiles + BK_A_STAGES * BK_A_BYTES;
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + BK_RING);  // [2]: MMAs of k-block kb done (A stage kb%2, B stage kb%4)
-  uint64_t *full_a = empty_bar + BK_A_STAGES;                           // [2]: A stage written (one arrival per producer warp)
-  uint64_t *full_b = full_a + BK_A_STAGES;                              // [4]: weight stage landed
-  uint64_t *done_bar = full_b + BK_B_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
-  float *coef_a = reinterpret_cast<float *>(tiles + BK_RING + 256);     // [3][TC_KMAX]
-  __shared__ float red[2][TC_THREADS / 32][32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs (see gemm_tc_kernel)
-  const int ntn = (g.N + TN - 1) / TN;
-  const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
-  const int m0 = m_tile * TM, n0 = n_tile * TN;
-  const int num_kb = (g.K + TK - 1) / TK;
-  const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
-  trace_stamp(g, blockIdx.x, 0, smid());
-  trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
-
-  if (tid == 0) {
-    for (int s = 0; s < BK_A_STAGES; ++s) {
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&full_a[s], TC_THREADS / 32);
-    }
-    for (int s = 0; s < BK_B_STAGES; ++s) mbar_init(&full_b[s], 1);
-    mbar_init(done_bar, 1);
-    mbar_fence_init();
-    fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
-    for (int kb = 0; kb < BK_B_STAGES && kb < num_kb; ++kb) {
-      mbar_expect_tx(&full_b[kb], BK_B_BYTES);
-      bulk_g2s(ring_b + kb * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[kb]);
-    }
-  }
-  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-
-  const uint32_t idesc = idesc_tf32(TM, TN, false);
-  constexpr int R = TC_ROWS_PER_THREAD;
-  const int chunk = tid & 7, rsub = tid >> 3;
-  uint32_t off[R];
-  RowCtx ca[R];
-  // A prefetch: DEPTH k-blocks ahead of the one being staged (register sets rr[0] = current .. rr[DEPTH])
-  // k-blocks of A in flight per thread beyond the current one (96 registers with 17 warps; DYPOOL chunks carry 9)
-  constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 1 : 2;
-  Raw rr[DEPTH + 1][R];
-  if (producer) {
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      off[i] = sw128_offset(rsub + 64 * i, chunk);
-      ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
-    }
-#pragma unroll
-    for (int d = 0; d < DEPTH; ++d)
-#pragma unroll
-      for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
-    stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
-  trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
-
-  auto issue_mmas = [&](int kb) {  // lane 0 of the MMA warp
-    const int sa = kb % BK_A_STAGES, sb = kb % BK_B_STAGES;
-    mbar_wait_guarded(&full_a[sa], (kb / BK_A_STAGES) & 1);
-    mbar_wait_guarded(&full_b[sb], (kb / BK_B_STAGES) & 1);
-    tc_fence_after_sync();
-    const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-    const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
-    const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
-    if (g.debug != 1 || kb == 0) {
-#pragma unroll
-      for (int ks = 0; ks < TK / 8; ++ks) {
-        const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-        mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-        mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-        mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
-      }
-    }
-    mma_commit(&empty_bar[sa]);
-    if (kb == num_kb - 1) mma_commit(done_bar);
-  };
-  if (!producer) {
-    if (lane == 0)
-      for (int kb = 0; kb < num_kb; ++kb) issue_mmas(kb);
-  } else {
-    // The prefetch register sets are addressed with compile-time indices (loop unrolled by the number of
-    // sets): rotating them with register copies would make every iteration wait for the loads it has just
-    // issued -- a move out of a register with a load in flight stalls until the data is back.
-    constexpr int NSET = DEPTH + 1;
-    for (int kb0 = 0; kb0 < num_kb; kb0 += NSET) {
-#pragma unroll
-      for (int u = 0; u < NSET; ++u) {
-        const int kb = kb0 + u;
-        if (kb >= num_kb) break;
-        const int sa = kb % BK_A_STAGES;
-        // 1. A loads of k-block kb + DEPTH in flight
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-          rr[(u + DEPTH) % NSET][i] =
-              fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
-        // 2. MMAs of k-block kb - 3 done: A stage sa is free, and so is the weight stage that k-block read, which
-        //    thread 0 refills with k-block kb (the first three were requested in the prologue)
-        if (kb >= BK_A_STAGES) {
-          mbar_wait_guarded(&empty_bar[sa], ((kb / BK_A_STAGES) - 1) & 1);
-          if (tid == 0) {
-            mbar_expect_tx(&full_b[sa], BK_B_BYTES);
-            bulk_g2s(ring_b + sa * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[sa]);
-          }
-        }
-        // 3. transform + split + store A, hand the stage to the MMA thread (one arrival per warp)
-        unsigned char *st = ring_a + sa * BK_A_BYTES;
-        if (g.debug != 2) {
-#pragma unroll
-          for (int i = 0; i < R; ++i) {
-            const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[u][i], coef_a, TC_KMAX, 0);
-            float4 hi, lo;
-            split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-            split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-            *reinterpret_cast<float4 *>(st + off[i]) = hi;
-            *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[sa]);
-      }
-    }
-    float4 yv[8];
-    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
-    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
-    tc_fence_after_sync();
-    trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
-    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
-  trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
-  trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
-}
-
-// ---- forward / data-gradient kernel with the A operand in tensor memory -------------------------------------
-// Measured on gemm_tc_bulk_kernel (profiles/c5_gemm_floor.txt): a k-block costs ~1.0 us against 0.40 us of MMA
-// time, and the same loop with the MMAs removed still needs 0.7 us -- the producer -> MMA-thread -> producer
-// hand-over of a shared-memory A stage (proxy fence, barrier round trip) is ~1.4 us long and a 2-stage ring
-// hides only half of it; the 192 KB of shared memory are full, so the ring cannot get deeper there.  The A
-// operand is produced in REGISTERS anyway (row source + hi/lo split), so this kernel writes it straight into
-// tensor memory with tcgen05.st (thread = tile row = TMEM lane, 8 consecutive k columns per warp quarter) and
-// the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc): no shared-memory traffic and no proxy fence for
-// A, 6 A stages in the 384 TMEM columns next to the accumulator, and all of shared memory for a 6-stage ring
-// of the bulk-copied weight image.  Shared-memory traffic per k-block drops from 160 KB to 80 KB.
-// All 16 warps are producers + epilogue; thread 0 additionally loads the weight stages and issues the MMAs.
-constexpr int TS_A_STAGES = 6, TS_B_STAGES = 6;
-constexpr int TS_THREADS = TC_THREADS;
-constexpr uint32_t TS_TMEM_COLS = 512, TS_A_COL0 = 128, TS_A_STAGE_COLS = 64;  // per stage: 32 hi + 32 lo columns
-constexpr int TS_RING = TS_B_STAGES * BK_B_BYTES;
-constexpr int TS_SMEM = TS_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
-
-template <int AKIND, int EPI>
-__global__ void __launch_bounds__(TS_THREADS, 1)
-gemm_tc_ts_kernel(const __grid_constant__ GemmArgs g) {
-  pdl_prologue();
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char *ring_b = tiles;
-  uint64_t *empty_a = reinterpret_cast<uint64_t *>(tiles + TS_RING);  // [6] MMAs that read A stage s have completed
-  uint64_t *full_a = empty_a + TS_A_STAGES;                           // [6] A stage written (one arrival per producer warp)
-  uint64_t *empty_b = full_a + TS_A_STAGES;                           // [6] MMAs that read weight stage s have completed
-  uint64_t *full_b = empty_b + TS_B_STAGES;                           // [6] weight stage landed
-  uint64_t *done_bar = full_b + TS_B_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
-  float *coef_a = reinterpret_cast<float *>(tiles + TS_RING + 256);   // [3][TC_KMAX]
-  __shared__ float red[2][TC_THREADS / 32][32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr bool producer = true;
-  const int ntn = (g.N + TN - 1) / TN;
-  const int m_tile = blockIdx.x / ntn, n_tile = blockIdx.x - m_tile * ntn;
-  const int m0 = m_tile * TM, n0 = n_tile * TN;
-  const int num_kb = (g.K + TK - 1) / TK;
-  const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
-  trace_stamp(g, blockIdx.x, 0, smid());
-  trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
-
-  if (tid == 0) {
-    for (int s = 0; s < TS_A_STAGES; ++s) {
-      mbar_init(&empty_a[s], 1);
-      mbar_init(&full_a[s], TC_THREADS / 32);
-    }
-    for (int s = 0; s < TS_B_STAGES; ++s) {
-      mbar_init(&empty_b[s], 1);
-      mbar_init(&full_b[s], 1);
-    }
-    mbar_init(done_bar, 1);
-    mbar_fence_init();
-    fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
-  }
-  if (warp == 0) tmem_alloc<TS_TMEM_COLS>(tmem_slot);
-
-  const uint32_t idesc = idesc_tf32(TM, TN, false);
-  // producer mapping: thread = tile row 32*(warp%4) + lane (its TMEM lane), columns 8*(warp/4)..+7 of the k-block
-  constexpr int R = 2;
-  const int quarter = warp & 3, cgrp = (warp >> 2) & 3;
-  RowCtx ca;
-  constexpr int DEPTH = (AKIND == PN2_ROWS_DYPOOL || AKIND == PN2_ROWS_DY) ? 2 : 3;  // register budget: 96 per thread
-  Raw rr[DEPTH + 1][R];
-  auto col_of = [&](int kb, int j) { return kb < num_kb ? kb * TK + cgrp * 8 + 4 * j : 0x3fffffff; };
-  if (producer) {
-    ca = row_ctx<AKIND>(g.A, m0 + quarter * 32 + lane);
-#pragma unroll
-    for (int d = 0; d < DEPTH; ++d)
-#pragma unroll
-      for (int j = 0; j < R; ++j) rr[d][j] = fetch_raw<AKIND>(g.A, ca, col_of(d, j));
-    stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
-  trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
-
-  // thread 0 also loads the weight stages (one 32 KB bulk copy per k-block, TS_B_LEAD blocks ahead) and issues the MMAs
-  constexpr int TS_B_LEAD = TS_B_STAGES - 2;  // the stage being refilled was read two k-blocks ago: its MMAs are done
-  auto load_b = [&](int kb) {
-    const int s = kb % TS_B_STAGES;
-    if (kb >= TS_B_STAGES) mbar_wait_guarded(&empty_b[s], ((kb / TS_B_STAGES) - 1) & 1);
-    mbar_expect_tx(&full_b[s], BK_B_BYTES);
-    bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
-  };
-  auto issue_mmas = [&](int kb) {
-    const int sa = kb % TS_A_STAGES, sb = kb % TS_B_STAGES;
-    mbar_wait_guarded(&full_a[sa], (kb / TS_A_STAGES) & 1);
-    mbar_wait_guarded(&full_b[sb], (kb / TS_B_STAGES) & 1);
-    tc_fence_after_sync();
-    const uint32_t a_hi = tmem_d + TS_A_COL0 + sa * TS_A_STAGE_COLS, a_lo = a_hi + 32;
-    const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-    const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
-#pragma unroll
-    for (int ks = 0; ks < TK / 8; ++ks) {
-      const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-      mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
-      mma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, idesc, true);
-      mma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, idesc, true);
-    }
-    mma_commit(&empty_a[sa]);
-    mma_commit(&empty_b[sb]);
-    if (kb == num_kb - 1) mma_commit(done_bar);
-  };
-  if (tid == 0)
-    for (int kb = 0; kb < TS_B_LEAD && kb < num_kb; ++kb) load_b(kb);
-  {
-    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + TS_A_COL0 + cgrp * 8;
-    constexpr int NSET = DEPTH + 1;  // compile-time register-set indices, see gemm_tc_bulk_kernel
-    for (int kb0 = 0; kb0 < num_kb; kb0 += NSET) {
-#pragma unroll
-      for (int u = 0; u < NSET; ++u) {
-        const int kb = kb0 + u;
-        if (kb >= num_kb) break;
-        const int sa = kb % TS_A_STAGES;
-#pragma unroll
-        for (int j = 0; j < R; ++j) rr[(u + DEPTH) % NSET][j] = fetch_raw<AKIND>(g.A, ca, col_of(kb + DEPTH, j));
-        if (tid == 0 && kb + TS_B_LEAD < num_kb) load_b(kb + TS_B_LEAD);
-        if (kb >= TS_A_STAGES) {
-          mbar_wait_guarded(&empty_a[sa], ((kb / TS_A_STAGES) - 1) & 1);
-          tc_fence_after_sync();
-        }
-        float hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const float4 v = apply_raw<AKIND>(g.A, ca, kb * TK + cgrp * 8 + 4 * j, rr[u][j], coef_a, TC_KMAX, 0);
-          split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
-        }
-        const uint32_t dst = lane_base + sa * TS_A_STAGE_COLS;
-        tmem_st8(dst, hi);
-        tmem_st8(dst + 32, lo);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[sa]);
-        if (tid == 0) issue_mmas(kb);
-      }
-    }
-    float4 yv[8];
-    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
-    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
-    tc_fence_after_sync();
-    trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
-    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<TS_TMEM_COLS>(tmem_d);
-  trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
-  trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
-}
-
-template <int AKIND, int EPI>
-int launch_tc_ts(const GemmArgs &g, cudaStream_t stream) {
-  auto kernel = gemm_tc_ts_kernel<AKIND, EPI>;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (configured_dev != dev) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
-    configured_dev = dev;
-  }
-  const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
-  GemmArgs a = g;
-  gemm_trace_target(&a.trace, &a.trace_cap);
-  pn2::launch(kernel, dim3(grid), dim3(TS_THREADS), TS_SMEM, stream, a);
-  return check_launch("gemm_tc_ts_kernel");
-}
-
-// ---- persistent form of gemm_tc_bulk_kernel -------------------------------------------------------------------
-// The per-CTA trace (profiles/r1_c8_gemm_trace.txt) shows 1.5 us of prologue (barrier init, TMEM allocation,
-// coefficient staging) and 0.9 us of CTA turnaround per 128x128 tile next to a 4-10 us main loop.  Here one CTA per
-// SM walks over the tiles (n-tile fastest, so neighbouring CTAs share A rows through L2): the prologue is paid
-// once, barriers / TMEM / coefficients live for the whole kernel, ring stages and barrier phases are indexed by a
-// running k-block counter.  A: 2-stage ring, weights: 4-stage ring, requested two k-blocks ahead inside a tile.
-// The epilogue scratch aliases the rings, hence one 512-thread barrier per tile after the epilogue.
-// Tiles are handed out dynamically (thread 0 draws tickets from a global counter one tile ahead and publishes
-// them through shared memory + an mbarrier for the MMA thread): the geometry stream's FPS cluster occupies 16 SMs
-// for most of a forward pass, and with a static tile list the CTAs that start late became a tail.  The counter
-// resets itself: the CTA that draws the last of the ntiles + gridDim.x tickets knows nobody will draw again.
+// Dynamic tile scheduler of the persistent kernel: thread 0 of a CTA draws tickets from a global counter (the geometry
+// stream's FPS cluster occupies 16 SMs for most of a forward pass; with a static tile list the CTAs that start late
+// became a tail).  The counter resets itself: the CTA that makes the last draw of the grid knows nobody draws again.
 __device__ int g_tile_counters[1024];
-constexpr int PB_A_STAGES = 2, PB_B_STAGES = 4;
-constexpr int PB_RING = PB_A_STAGES * BK_A_BYTES + PB_B_STAGES * BK_B_BYTES;
-constexpr int PB_SMEM = PB_RING + 1024 /*align*/ + 256 /*barriers*/ + TC_COEF_FLOATS * 4;
+
+// PN2_TC_PERSISTENT_SPARE SMs are left to the geometry stream (FPS / ball query of the next level run underneath
+// the MLP; a persistent grid on every SM would make them wait for a whole GEMM)
+inline int persistent_spare() {
+  static const int spare = [] {
+    const char *e = getenv("PN2_TC_PERSISTENT_SPARE");
+    return e ? atoi(e) : 8;  // measured: 0 -> 4.11, 8 -> 3.92, 16 -> 3.93 ms per step (profiles/r1_bench_*spare*)
+  }();
+  return spare;
+}
+
+// one self-resetting ticket counter per launch in flight (a captured graph keeps replaying the slot it was captured with)
+int *tile_counter_slot(int dev) {
+  static thread_local int *counters = nullptr;
+  static thread_local int counters_dev = -1;
+  static std::atomic<unsigned> next_slot{0};  // process-wide: launches from different threads / streams never share a slot
+  if (counters_dev != dev) {
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_tile_counters) != cudaSuccess) return nullptr;
+    counters = static_cast<int *>(p);
+    counters_dev = dev;
+  }
+  return counters + (next_slot.fetch_add(1, std::memory_order_relaxed) & 1023u);
+}
+
+// ---- persistent forward / dgrad kernel: async raw ring -> tensor-memory A operand -----------------------------------
+// Round-2 measurements (tools/mma_floor.cu, profiles/r2_mma_floor.txt): twelve kind::tf32 128x128x8 MMAs -- one 32-wide
+// k-block of the 3xTF32 scheme -- take 768 cycles (0.39 us) in SS *and* TS form, with or without concurrent
+// shared-memory store traffic, so the 1.0 / 1.25 us per k-block of gemm_tc_pbulk_kernel is NOT operand bandwidth: it
+// is the producers.  Their global loads were prefetched through registers, and the depth that survives register
+// rotation / the 96-register cap is about one k-block, i.e. one memory latency (~1 us) per k-block.
+//
+// Here the loads no longer pass through registers:
+//   * every producer thread issues its 16-byte pieces of the next k-blocks with cp.async (LDGSTS) into a RAW ring in
+//     shared memory (5 stages of 16 KB for plain / BatchNorm / gather sources, 3 stages of 32-36 KB for the
+//     BatchNorm-backward sources that read y and dz), coalesced (8 lanes = one 128-byte row segment), completion
+//     signalled per stage on an mbarrier (cp.async.mbarrier.arrive.noinc) -- 64-96 KB in flight per SM, independent of
+//     the register allocator; the ring runs ACROSS tile boundaries (tickets are drawn two tiles ahead), so the first
+//     k-blocks of the next tile are in flight during the epilogue of the current one;
+//   * the transform (gather / BN+ReLU / BN backward + pool routing) and the hi/lo split read the raw stage with
+//     thread = tile row (16-byte chunks XOR-swizzled by row: conflict-free) and write the operand straight into TENSOR
+//     MEMORY (tcgen05.st, thread = TMEM lane); the MMAs take A from TMEM (TS form).  The A operand therefore needs no
+//     shared memory at all, which is what pays for the raw ring; 6 A stages live in the 384 TMEM columns next to the
+//     accumulator;
+//   * weights: the pre-split image, one 32 KB bulk copy per k-block, 3-4 stage ring (as before).
+// 16 producer warps + one MMA warp (lane 0 issues) + one weight-loader warp (lane 0 issues the bulk copies, so that
+// waiting for a free weight stage never stalls a producer), one CTA per SM, dynamic tile tickets.
+constexpr int AS_NA = 6;
+constexpr int AS_CTA_THREADS = TC_THREADS + 64;
+constexpr uint32_t AS_TMEM_COLS = 512, AS_A_COL0 = 128, AS_A_STAGE_COLS = 64;  // per A stage: 32 hi + 32 lo columns
+constexpr int AS_ARG_BYTES = TM * TK;                                             // uint8 arg-max slots of a k-block
+
+template <int AKIND>
+struct AsCfg {
+  static constexpr bool kDz = AKIND == PN2_ROWS_DY || AKIND == PN2_ROWS_DYPOOL;
+  static constexpr bool kArg = AKIND == PN2_ROWS_DYPOOL;
+  static constexpr bool kCoef = !(AKIND == PN2_ROWS_PLAIN || AKIND == PN2_ROWS_GATHER);
+  static constexpr int kRawBytes = TILE_BYTES * (kDz ? 2 : 1) + (kArg ? AS_ARG_BYTES : 0);
+  static constexpr int kNR = kDz ? 3 : (kCoef ? 4 : 5);  // raw stages
+  static constexpr int kNB = kDz ? 3 : 4;                // weight stages
+  static constexpr int kCoefK = kCoef ? TC_KMAX : 0;     // largest K with per-channel coefficient vectors
+  static constexpr int kRing = kNB * BK_B_BYTES + kNR * kRawBytes;
+  static constexpr int kSmem = kRing + 1024 /*align*/ + 512 /*barriers, tickets*/ + 3 * kCoefK * 4;
+  static_assert(kSmem + 4096 /*static: statistics partials*/ <= 232448, "shared memory budget");
+  static_assert(kNB * BK_B_BYTES >= (TC_THREADS / 32) * 32 * 36 * 4, "epilogue scratch aliases the weight ring");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed (the count is part of the init value)
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds4(const unsigned char *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// what the ISSUING thread needs of a row: where it lives
+struct IssueCtx {
+  bool valid;
+  size_t off, goff;
+};
+template <int AKIND>
+__device__ __forceinline__ IssueCtx issue_ctx(const pn2_rows &s, int row) {
+  IssueCtx c;
+  c.valid = row < s.rows;
+  c.off = 0; c.goff = 0;
+  if (!c.valid) return c;
+  if (AKIND == PN2_ROWS_GATHER) {
+    const int cloud = row / (s.npoint * s.nsample);
+    c.off = (static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row)) * s.ld;
+  } else {
+    c.off = static_cast<size_t>(row) * s.ld;
+    if (AKIND == PN2_ROWS_DYPOOL) c.goff = static_cast<size_t>(row / s.group) * s.ld;
+  }
+  return c;
+}
+// what the TRANSFORMING thread needs of its row: validity, pool slot, local coordinates of a gathered neighbour
+struct ConsCtx {
+  bool valid;
+  int slot;
+  float gx, gy, gz;
+};
+template <int AKIND>
+__device__ __forceinline__ ConsCtx cons_ctx(const pn2_rows &s, int row, bool want_xyz) {
+  ConsCtx c;
+  c.valid = row < s.rows;
+  c.slot = 0; c.gx = c.gy = c.gz = 0.f;
+  if (!c.valid) return c;
+  if (AKIND == PN2_ROWS_DYPOOL) c.slot = row % s.group;
+  if (AKIND == PN2_ROWS_GATHER && want_xyz && s.use_xyz) {
+    const int cloud = row / (s.npoint * s.nsample), centre = row / s.nsample;
+    const size_t src = static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row);
+    const float *p = s.xyz + src * 3, *q = s.centres + static_cast<size_t>(centre) * 3;
+    c.gx = __fdiv_rn(__fsub_rn(__ldg(p + 0), __ldg(q + 0)), s.inv_scale);  // pointnet2_utils.py:350-352
+    c.gy = __fdiv_rn(__fsub_rn(__ldg(p + 1), __ldg(q + 1)), s.inv_scale);
+    c.gz = __fdiv_rn(__fsub_rn(__ldg(p + 2), __ldg(q + 2)), s.inv_scale);
+  }
+  return c;
+}
 
 template <int AKIND, int EPI>
-__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
-gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(AS_CTA_THREADS, 1)
+gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
+  using Cfg = AsCfg<AKIND>;
+  constexpr int NR = Cfg::kNR, NB = Cfg::kNB, NA = AS_NA;
   pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char *ring_a = tiles, *ring_b = tiles + PB_A_STAGES * BK_A_BYTES;
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + PB_RING);  // [2] MMAs of the k-block done (A stage, B stage)
-  uint64_t *full_a = empty_bar + PB_A_STAGES;                           // [2] A stage written (one arrival per producer warp)
-  uint64_t *full_b = full_a + PB_A_STAGES;                              // [4] weight stage landed
-  uint64_t *done_bar = full_b + PB_B_STAGES;                            // accumulator of the tile complete
-  uint64_t *tile_bar = done_bar + 1;                                    // next tile ticket published
+  unsigned char *ring_b = tiles, *ring_r = tiles + NB * BK_B_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + Cfg::kRing);
+  uint64_t *full_b = bars, *empty_b = full_b + NB;            // weight stage landed / its MMAs done
+  uint64_t *raw_full = empty_b + NB, *raw_empty = raw_full + NR;  // raw stage landed (512 async arrivals) / read (16 warps)
+  uint64_t *full_a = raw_empty + NR, *empty_a = full_a + NA;  // A stage in tensor memory written (16 warps) / its MMAs done
+  uint64_t *done_bar = empty_a + NA, *tile_bar = done_bar + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tile_bar + 1);
-  float *coef_a = reinterpret_cast<float *>(tiles + PB_RING + 256);     // [3][TC_KMAX]
+  int *ticket = reinterpret_cast<int *>(tmem_slot + 1);       // [8] ticket[ti & 7] = tile of this CTA's ti-th iteration
+  float *coef_a = reinterpret_cast<float *>(tiles + Cfg::kRing + 512);  // [3][kCoefK]
   __shared__ float red[2][TC_THREADS / 32][32];
-  __shared__ int ticket[2];  // ticket[ti & 1] = tile of this CTA's ti-th iteration (>= ntiles: stop)
+  static_assert((2 * 4 + 2 * 6 + 2 * AS_NA + 2) * 8 + 4 + 32 <= 512, "barrier block");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs
+  const bool producer = warp < TC_THREADS / 32;
   const int ntn = (g.N + TN - 1) / TN;
   const int ntiles = ((g.M + TM - 1) / TM) * ntn;
   const int num_kb = (g.K + TK - 1) / TK;
+  const int last_ticket = ntiles + 5 * static_cast<int>(gridDim.x) - 1;  // every CTA draws exactly five tickets past the end
   trace_stamp(g, blockIdx.x, 0, smid());
   trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
 
+  auto draw = [&]() {  // thread 0
+    const int t = atomicAdd(g.tile_counter, 1);
+    if (t == last_ticket) *g.tile_counter = 0;  // the last draw of the whole grid: nobody draws again
+    return t;
+  };
   if (tid == 0) {
-    for (int s = 0; s < PB_A_STAGES; ++s) {
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&full_a[s], TC_THREADS / 32);
-    }
-    for (int s = 0; s < PB_B_STAGES; ++s) mbar_init(&full_b[s], 1);
+    for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], TC_THREADS); mbar_init(&raw_empty[s], TC_THREADS / 32); }
+    for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], TC_THREADS / 32); mbar_init(&empty_a[s], 1); }
     mbar_init(done_bar, 1);
     mbar_init(tile_bar, 1);
     mbar_fence_init();
     fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
-    ticket[0] = atomicAdd(g.tile_counter, 1);
+    int t[5];
+    for (int i = 0; i < 5; ++i) t[i] = atomicAdd(g.tile_counter, 1);  // five independent atomics in flight together
+    for (int i = 0; i < 5; ++i) {
+      if (t[i] == last_ticket) *g.tile_counter = 0;
+      ticket[i] = t[i];
+    }
   }
-  const int last_ticket = ntiles + static_cast<int>(gridDim.x) - 1;
-  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (producer) stage_coef<AKIND>(g.A, coef_a, TC_KMAX, 0, min(g.K, TC_KMAX), tid);
+  if (warp == 0) tmem_alloc<AS_TMEM_COLS>(tmem_slot);
+  if (producer && Cfg::kCoef) stage_coef<AKIND>(g.A, coef_a, Cfg::kCoefK, 0, min(g.K, Cfg::kCoefK), tid);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -894,167 +696,265 @@ gemm_tc_pbulk_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
   if (!producer) {
-    if (lane == 0) {  // ---- MMA thread: the k-blocks of all of this CTA's tiles form one stream `it`
+    // tile_bar arrival #ti is made by thread 0 when the producers START tile ti: the epilogue of tile ti-1 (whose
+    // scratch aliases the weight ring) is over and ticket[ti & 3] has long been written.  Both service threads below
+    // wait for it once per tile; thread 0 cannot get two arrivals ahead of them (arrival #ti+1 needs the MMAs of tile ti).
+    if (warp == TC_THREADS / 32) {  // ---- MMA warp, converged: the k-blocks of all of this CTA's tiles form one stream `it`
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);  // warp-uniform for the compiler too
       int it = 0;
       for (int ti = 0;; ++ti) {
-        if (ti > 0) mbar_wait_guarded(tile_bar, (ti - 1) & 1);
-        if (ticket[ti & 1] >= ntiles) break;
+        mbar_wait_guarded(tile_bar, ti & 1);
+        if (__shfl_sync(0xffffffffu, ticket[ti & 7], 0) >= ntiles) break;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int sa = it & (PB_A_STAGES - 1), sb = it & (PB_B_STAGES - 1);
-          mbar_wait_guarded(&full_a[sa], (it >> 1) & 1);  // the first block of a tile arrives only after every
-          mbar_wait_guarded(&full_b[sb], (it >> 2) & 1);  // warp has drained the previous accumulator
+          const int sa = it % NA, sb = it % NB;
+          mbar_wait_guarded(&full_a[sa], (it / NA) & 1);
+          if (kb == 0 && lane == 0) tile_stamp(ti, 5);
+          mbar_wait_guarded(&full_b[sb], (it / NB) & 1);
           tc_fence_after_sync();
-          const uint32_t abase = smem_addr(ring_a + sa * BK_A_BYTES), bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-          const uint64_t a_hi = smem_desc_sw128(abase), a_lo = smem_desc_sw128(abase + TILE_BYTES);
+          if (kb == 0 && lane == 0) tile_stamp(ti, 6);
+          const uint32_t a_hi = tmem_u + AS_A_COL0 + sa * AS_A_STAGE_COLS, a_lo = a_hi + 32;
+          const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
           const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < TK / 8; ++ks) {
-            const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, true);
-            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, true);
+            for (int ks = 0; ks < TK / 8; ++ks) {
+              const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+              mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
+              mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_lo + adv, idesc, true);
+              mma_tf32_ts(tmem_u, a_lo + 8 * ks, b_hi + adv, idesc, true);
+            }
+            mma_commit(&empty_a[sa]);
+            mma_commit(&empty_b[sb]);
+            if (kb == num_kb - 1) mma_commit(done_bar);
           }
-          mma_commit(&empty_bar[sa]);
-          if (kb == num_kb - 1) mma_commit(done_bar);
+          __syncwarp();
+        }
+      }
+    } else if (warp == TC_THREADS / 32 + 1 && lane == 0) {  // ---- weight loader: one 32 KB bulk copy per k-block
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        mbar_wait_guarded(tile_bar, ti & 1);
+        const int tile = ticket[ti & 7];
+        if (tile >= ntiles) break;
+        const int n_tile = tile % ntn;
+        const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % NB;
+          if (it >= NB) mbar_wait_guarded(&empty_b[s], ((it / NB) - 1) & 1);  // the MMAs that read this stage are done
+          if (kb == 0) tile_stamp(ti, 7);
+          mbar_expect_tx(&full_b[s], BK_B_BYTES);
+          bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
         }
       }
     }
   } else {
-    constexpr int R = TC_ROWS_PER_THREAD;
-    constexpr int DEPTH = AKIND == PN2_ROWS_DYPOOL ? 1 : 2;  // k-blocks of A in flight beyond the current one
+    // ---- producers.  What a k-block costs here is neither bandwidth nor the tensor pipe but the LENGTH of the per-warp
+    // instruction chain: with 18 warps per SM a warp issues a dependent instruction every ~5 cycles, and this loop
+    // (ring top-up, two barrier waits, shared-memory reads, transform, tcgen05.st + wait, fence + arrive) needs
+    // ~1800 cycles per k-block although a thread only moves 8 values (profiles/r2_tile_trace.txt).  Ring positions and
+    // phase bits are carried incrementally instead of computed.  kPair = true handles TWO k-blocks per iteration (half
+    // the barrier round trips per k-block); measured SLOWER (63.9 vs 49.1 us on 32768 x 256 -> 256: the MMA warp then
+    // receives its stages in bursts), so it stays off -- as does a variant with four warp groups owning every fourth
+    // k-block (2.6 us per group and k-block).  See DESIGN.md section 4 for what this leaves on the table.
+    constexpr bool kPair = false;
+    // issue mapping: 16-byte chunk `chunk` of rows rsub, rsub + 64 (8 consecutive lanes = one 128-byte row segment)
     const int chunk = tid & 7, rsub = tid >> 3;
-    uint32_t off[R];
+    // transform mapping: tile row 32*(warp%4) + lane (= this thread's TMEM lane), k columns 8*(warp/4) .. +7
+    const int quarter = warp & 3, cgrp = warp >> 2, crow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + AS_A_COL0 + cgrp * 8;
+    const bool xyz_mine = AKIND == PN2_ROWS_GATHER && ((g.A.feat_cols % TK) / 8) == cgrp;
+    const void *dummy = g.b_img;  // a valid address for zero-filling copies (src size 0 reads nothing)
+    // per-thread constants of the two mappings
+    const uint32_t ring_r_s = smem_addr(ring_r);
+    uint32_t ioff[2];   // issue: byte offset of (row rsub + 64 i, chunk) inside a raw x / dz tile
 #pragma unroll
-    for (int i = 0; i < R; ++i) off[i] = sw128_offset(rsub + 64 * i, chunk);
-    int it = 0;
+    for (int i = 0; i < 2; ++i) ioff[i] = (rsub + 64 * i) * 128 + ((chunk ^ ((rsub + 64 * i) & 7)) << 4);
+    uint32_t coff[2];   // transform: byte offset of (row crow, chunk 2 cgrp + j)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) coff[j] = crow * 128 + (((2 * cgrp + j) ^ (crow & 7)) << 4);
+
+    // ring cursors, carried incrementally: slot index, phase parity of the slot's CURRENT use, "has wrapped" flag
+    int c_sr = 0, c_pr = 0;               // consume side of the raw ring
+    int c_sa = 0, c_pa = 0, c_la = 0;     // A stages in tensor memory
+    int i_sr = 0, i_pr = 0, i_lr = 0;     // issue side of the raw ring
+    int il = 0, it = 0;                   // stream indices: next k-block to issue / to transform
+    int lt = 0, lkb = 0;                  // the load cursor's tile sequence number and k-block inside that tile
+    IssueCtx lc[2], nlc[2];               // issue contexts of the current tile / of the tile after it
+    ConsCtx cc, ncc;
+    bool have_next = false;
+    {
+      const int t0 = ticket[0];
+      if (t0 < ntiles) {
+        const int m0 = (t0 / ntn) * TM;
+        lc[0] = issue_ctx<AKIND>(g.A, m0 + rsub);
+        lc[1] = issue_ctx<AKIND>(g.A, m0 + rsub + 64);
+        cc = cons_ctx<AKIND>(g.A, m0 + crow, xyz_mine);
+      }
+    }
+    auto issue = [&](const IssueCtx (&c)[2], int kb) {  // this thread's copies of k-block kb into raw stage i_sr
+      if (i_lr) mbar_wait_guarded(&raw_empty[i_sr], i_pr ^ 1);
+      const uint32_t raw = ring_r_s + i_sr * Cfg::kRawBytes;
+      const int c4 = kb * TK + chunk * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        bool ok = c[i].valid && c4 < g.A.cols;
+        if (AKIND == PN2_ROWS_GATHER) ok = ok && c4 < g.A.feat_cols;
+        cp_async16(raw + ioff[i], ok ? static_cast<const void *>(g.A.x + c[i].off + c4) : dummy, ok ? 16 : 0);
+        if (Cfg::kDz) {
+          const float *dz = g.A.dz + (AKIND == PN2_ROWS_DYPOOL ? c[i].goff : c[i].off) + c4;
+          cp_async16(raw + TILE_BYTES + ioff[i], ok ? static_cast<const void *>(dz) : dummy, ok ? 16 : 0);
+        }
+        if (Cfg::kArg)
+          cp_async4(raw + 2 * TILE_BYTES + (chunk * TM + rsub + 64 * i) * 4,
+                    ok ? static_cast<const void *>(g.A.arg + c[i].goff + c4) : dummy, ok ? 4 : 0);
+      }
+      cp_async_arrive(&raw_full[i_sr]);
+      if (++i_sr == NR) { i_sr = 0; i_pr ^= 1; i_lr = 1; }
+      ++il;
+      if (++lkb == num_kb) { lkb = 0; ++lt; }
+    };
+
     for (int ti = 0;; ++ti) {
-      const int tile = ticket[ti & 1];
+      const int tile = ticket[ti & 7];
       if (tile >= ntiles) {
-        if (tid == 0 && tile == last_ticket) *g.tile_counter = 0;  // every CTA has drawn its last ticket
+        if (tid == 0) mbar_arrive(tile_bar);  // releases the MMA / weight-loader warps, which then see the end ticket too
         break;
       }
-      if (tid == 0) {  // draw the next tile now; everybody reads it after this tile's closing barrier
-        ticket[(ti + 1) & 1] = atomicAdd(g.tile_counter, 1);
-        mbar_arrive(tile_bar);
+      const int next_tile = ticket[(ti + 1) & 7];
+      if (tid == 0) {
+        mbar_arrive(tile_bar);  // arrival #ti: tile ti has started
+        tile_stamp(ti, 0);
       }
       const int m_tile = tile / ntn, n_tile = tile - m_tile * ntn;
       const int m0 = m_tile * TM, n0 = n_tile * TN;
-      const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
-      auto load_b = [&](int kb, int stream) {  // thread 0: weight stage of k-block kb (stream index `stream`)
-        const int s = stream & (PB_B_STAGES - 1);
-        mbar_expect_tx(&full_b[s], BK_B_BYTES);
-        bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
-      };
-      if (tid == 0)
-        for (int kb = 0; kb < 2 && kb < num_kb; ++kb) load_b(kb, it + kb);  // every earlier MMA has completed (done_bar)
-      RowCtx ca[R];
-      Raw rr[DEPTH + 1][R];
-#pragma unroll
-      for (int i = 0; i < R; ++i) ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
-#pragma unroll
-      for (int d = 0; d < DEPTH; ++d)
-#pragma unroll
-        for (int i = 0; i < R; ++i) rr[d][i] = fetch_raw<AKIND>(g.A, ca[i], d < num_kb ? d * TK + chunk * 4 : 0x3fffffff);
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int sa = it & (PB_A_STAGES - 1);
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-          rr[DEPTH][i] = fetch_raw<AKIND>(g.A, ca[i], kb + DEPTH < num_kb ? (kb + DEPTH) * TK + chunk * 4 : 0x3fffffff);
-        // MMAs of stream block it - 2 done: A stage sa and weight stage (it + 2) % 4 are free
-        if (it >= PB_A_STAGES) mbar_wait_guarded(&empty_bar[sa], ((it >> 1) - 1) & 1);
-        if (tid == 0 && kb + 2 < num_kb) load_b(kb + 2, it + 2);
-        unsigned char *st = ring_a + sa * BK_A_BYTES;
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const float4 va = apply_raw<AKIND>(g.A, ca[i], kb * TK + chunk * 4, rr[0][i], coef_a, TC_KMAX, 0);
-          float4 hi, lo;
-          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + TILE_BYTES + off[i]) = lo;
+      // contexts of the NEXT tile, resolved one tile ahead so that their (dependent) loads are long back when needed
+      have_next = next_tile < ntiles;
+      if (have_next) {
+        const int nm0 = (next_tile / ntn) * TM;
+        nlc[0] = issue_ctx<AKIND>(g.A, nm0 + rsub);
+        nlc[1] = issue_ctx<AKIND>(g.A, nm0 + rsub + 64);
+        ncc = cons_ctx<AKIND>(g.A, nm0 + crow, xyz_mine);
+      }
+      RowCtx rc;
+      rc.valid = cc.valid; rc.off = 0; rc.goff = 0; rc.slot = cc.slot; rc.gx = cc.gx; rc.gy = cc.gy; rc.gz = cc.gz;
+      for (int kb = 0; kb < num_kb; kb += kPair ? 2 : 1) {
+        const bool two = kPair && kb + 1 < num_kb;  // warp-uniform: a pair, or a single k-block
+        // 1. keep the raw ring full: up to NR - 1 k-blocks beyond the first one of this pair, into the next tile if need be
+        while (il - it < NR - 1) {
+          if (lt == ti) issue(lc, lkb);
+          else if (lt == ti + 1 && have_next) issue(nlc, lkb);
+          else break;
         }
-        fence_proxy_async_smem();
+        // 2. the pair's raw stages have landed (all 512 threads' copies): read this thread's pieces, release the stages
+        const int sr0 = c_sr, pr0 = c_pr;
+        if (++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
+        const int sr1 = c_sr, pr1 = c_pr;
+        if (two && ++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
+        Raw rw[2][2];
+        mbar_wait_guarded(&raw_full[sr0], pr0);
+        if (two) mbar_wait_guarded(&raw_full[sr1], pr1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const unsigned char *raw = ring_r + (u ? sr1 : sr0) * Cfg::kRawBytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            rw[u][j].x = zero4(); rw[u][j].d = zero4(); rw[u][j].a = make_uchar4(0, 0, 0, 0);
+            if (u == 0 || two) {
+              rw[u][j].x = lds4(raw + coff[j]);
+              if (Cfg::kDz) rw[u][j].d = lds4(raw + TILE_BYTES + coff[j]);
+              if (Cfg::kArg) rw[u][j].a = *reinterpret_cast<const uchar4 *>(raw + 2 * TILE_BYTES + ((2 * cgrp + j) * TM + crow) * 4);
+            }
+          }
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[sa]);
+        if (lane == 0) {  // the stages may be refilled once all 16 warps have read them
+          mbar_arrive(&raw_empty[sr0]);
+          if (two) mbar_arrive(&raw_empty[sr1]);
+        }
+        // 3. transform + split
+        float hi[2][8], lo[2][8];
 #pragma unroll
-        for (int d = 0; d < DEPTH; ++d)
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int i = 0; i < R; ++i) rr[d][i] = rr[d + 1][i];
+          for (int j = 0; j < 2; ++j) {
+            const float4 v = apply_raw<AKIND>(g.A, rc, (kb + u) * TK + cgrp * 8 + 4 * j, rw[u][j], coef_a, Cfg::kCoefK, 0);
+            split_tf32(v.x, hi[u][4 * j + 0], lo[u][4 * j + 0]); split_tf32(v.y, hi[u][4 * j + 1], lo[u][4 * j + 1]);
+            split_tf32(v.z, hi[u][4 * j + 2], lo[u][4 * j + 2]); split_tf32(v.w, hi[u][4 * j + 3], lo[u][4 * j + 3]);
+          }
+        // 4. straight into tensor memory: the A stages of the pair are free once the MMAs that read them have completed
+        const int sa0 = c_sa, pa0 = c_pa, la0 = c_la;
+        if (++c_sa == NA) { c_sa = 0; c_pa ^= 1; c_la = 1; }
+        const int sa1 = c_sa, pa1 = c_pa, la1 = c_la;
+        if (two && ++c_sa == NA) { c_sa = 0; c_pa ^= 1; c_la = 1; }
+        if (la0) mbar_wait_guarded(&empty_a[sa0], pa0 ^ 1);
+        if (two && la1) mbar_wait_guarded(&empty_a[sa1], pa1 ^ 1);
+        if (la0 || la1) tc_fence_after_sync();
+        tmem_st8(lane_base + sa0 * AS_A_STAGE_COLS, hi[0]);
+        tmem_st8(lane_base + sa0 * AS_A_STAGE_COLS + 32, lo[0]);
+        if (two) {
+          tmem_st8(lane_base + sa1 * AS_A_STAGE_COLS, hi[1]);
+          tmem_st8(lane_base + sa1 * AS_A_STAGE_COLS + 32, lo[1]);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full_a[sa0]);
+          if (two) mbar_arrive(&full_a[sa1]);
+        }
+        it += two ? 2 : 1;
+        if (tid == 0 && kb == 0) tile_stamp(ti, 1);
+      }
+      if (tid == 0) {
+        tile_stamp(ti, 2);
+        // draw the ticket five tiles ahead -- here, where this thread would otherwise only wait for the accumulator (the
+        // atomic's ~1 us round trip at the START of a tile delayed warp 0 and with it everybody); everybody reads it
+        // after the closing barrier below
+        ticket[(ti + 5) & 7] = draw();
       }
       float4 yv[8];
       tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
-      if (num_kb > 0) mbar_wait_guarded(done_bar, ti & 1);
+      mbar_wait_guarded(done_bar, ti & 1);
       tc_fence_after_sync();
-      tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, num_kb > 0, yv);
+      if (tid == 0) tile_stamp(ti, 3);
+      tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, true, yv);  // scratch = the (idle) weight ring
       tc_fence_before_sync();   // this warp's TMEM reads are complete before the next tile's first MMA can be issued
-      producers_sync();         // the epilogue scratch aliases both rings
+      producers_sync();
+      if (tid == 0) tile_stamp(ti, 4);
+      cc = ncc;
+      lc[0] = nlc[0];
+      lc[1] = nlc[1];
     }
   }
   trace_stamp(g, blockIdx.x, 3, globaltimer_ns());
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
+  if (warp == 0) tmem_dealloc<AS_TMEM_COLS>(tmem_d);
   trace_stamp(g, blockIdx.x, 4, globaltimer_ns());
   trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
 }
 
 template <int AKIND, int EPI>
-int launch_tc_pbulk(const GemmArgs &g, cudaStream_t stream) {
-  auto kernel = gemm_tc_pbulk_kernel<AKIND, EPI>;
+int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
+  using Cfg = AsCfg<AKIND>;
+  auto kernel = gemm_tc_async_kernel<AKIND, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     configured_dev = dev;
   }
   const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
-  // PN2_TC_PERSISTENT_SPARE SMs are left to the geometry stream (FPS / ball query of the next level run underneath
-  // the MLP; a persistent grid on every SM would make them wait for a whole GEMM)
-  static const int spare = [] {
-    const char *e = getenv("PN2_TC_PERSISTENT_SPARE");
-    return e ? atoi(e) : 8;  // measured: 0 -> 4.11, 8 -> 3.92, 16 -> 3.93 ms per step (profiles/r1_bench_*spare*)
-  }();
-  const int sms = sm_count() - spare > 1 ? sm_count() - spare : 1;
+  const int sms = sm_count() - persistent_spare() > 1 ? sm_count() - persistent_spare() : 1;
   const int grid = ntiles < sms ? ntiles : sms;
   GemmArgs a = g;
   gemm_trace_target(&a.trace, &a.trace_cap);
-  // one counter slot per launch in flight (a captured graph keeps replaying the slot it was captured with)
-  static thread_local int *counters = nullptr;
-  static thread_local int counters_dev = -1;
-  static std::atomic<unsigned> next_slot{0};  // process-wide: launches from different threads / streams never share a slot
-  if (counters_dev != dev) {
-    void *p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_tile_counters) != cudaSuccess) return check_launch("gemm_tc_pbulk_kernel(counters)");
-    counters = static_cast<int *>(p);
-    counters_dev = dev;
-  }
-  a.tile_counter = counters + (next_slot.fetch_add(1, std::memory_order_relaxed) & 1023u);
-  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), PB_SMEM, stream, a);
-  return check_launch("gemm_tc_pbulk_kernel");
-}
-
-template <int AKIND, int EPI>
-int launch_tc_bulk(const GemmArgs &g, cudaStream_t stream) {
-  auto kernel = gemm_tc_bulk_kernel<AKIND, EPI>;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (configured_dev != dev) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM);
-    configured_dev = dev;
-  }
-  const unsigned grid = static_cast<unsigned>((g.M + TM - 1) / TM) * static_cast<unsigned>((g.N + TN - 1) / TN);
-  GemmArgs a = g;
-  gemm_trace_target(&a.trace, &a.trace_cap);
-  static const int debug = [] {
-    const char *e = getenv("PN2_TC_DEBUG");
-    return e ? atoi(e) : 0;
-  }();
-  a.debug = debug;
-  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), BK_SMEM, stream, a);
-  return check_launch("gemm_tc_bulk_kernel");
+  a.tile_counter = tile_counter_slot(dev);
+  if (a.tile_counter == nullptr) return check_launch("gemm_tc_async_kernel(counters)");
+  pn2::launch(kernel, dim3(grid), dim3(AS_CTA_THREADS), Cfg::kSmem, stream, a);
+  return check_launch("gemm_tc_async_kernel");
 }
 
 template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
@@ -1116,21 +1016,9 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
     return e == nullptr || e[0] != '0';
   }();
   const bool use_bulk = bulk_on && g.b_img != nullptr;
-  // PN2_TC_TS=1 selects the A-in-tensor-memory variant (correct, but measured slower: profiles/c7_gemm_trace_ts.txt)
-  static const bool ts_on = [] {
-    const char *e = getenv("PN2_TC_TS");
-    return e != nullptr && e[0] == '1';
-  }();
-  // PN2_TC_PERSISTENT=0 launches one CTA per tile (gemm_tc_bulk_kernel) instead of the persistent form
-  static const bool persistent = [] {
-    const char *e = getenv("PN2_TC_PERSISTENT");
-    return e == nullptr || e[0] != '0';
-  }();
 #define PN2_TC_CASE(AK, EP)                                                                     \
   if (akind == AK && epi == EP)                                                                 \
-    return !use_bulk ? launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream)                   \
-           : ts_on   ? launch_tc_ts<AK, EP>(g, stream)                                          \
-           : persistent ? launch_tc_pbulk<AK, EP>(g, stream) : launch_tc_bulk<AK, EP>(g, stream);
+    return !use_bulk ? launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream) : launch_tc_async<AK, EP>(g, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)
@@ -1162,6 +1050,13 @@ int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream)
 }
 
 }  // namespace pn2
+
+PN2_EXPORT int pn2_debug_gemm_trace2(unsigned long long *device_buf, int ctas) {
+  int n = device_buf ? ctas : 0;
+  if (cudaMemcpyToSymbol(pn2::g_trace2, &device_buf, sizeof(device_buf)) != cudaSuccess) return pn2::check_launch("pn2_debug_gemm_trace2");
+  if (cudaMemcpyToSymbol(pn2::g_trace2_ctas, &n, sizeof(n)) != cudaSuccess) return pn2::check_launch("pn2_debug_gemm_trace2");
+  return PN2_OK;
+}
 
 PN2_EXPORT int pn2_debug_gemm_trace(unsigned long long *device_buf, int ctas) {
   pn2::g_trace_buf = device_buf;

@@ -106,7 +106,6 @@ struct GemmArgs {
   unsigned long long *trace;
   int trace_cap;
   int *tile_counter;  // persistent GEMM: dynamic tile scheduler (self-resetting ticket counter)
-  int debug;  // development aid (PN2_TC_DEBUG): 1 = skip the MMAs, 2 = skip operand staging (results are garbage)
 };
 
 }  // namespace
@@ -116,11 +115,6 @@ constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
-// first-layer kernels for K <= 16 (mlp_smallk.cu)
-bool smallk_eligible(int akind, int kp, int np);
-int smallk_wgrad_splits(int rows);
-int smallk_forward_launch(const void *gemm_args, cudaStream_t stream);
-int smallk_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 void gemm_trace_target(unsigned long long **buf, int *cap);
 
 }  // namespace pn2

@@ -158,12 +158,26 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {
                : "memory");
 }
 
-// fp32 -> (hi, lo) with hi = nearest tf32 and lo = v - hi (exact); the tensor core keeps lo's top 19 bits
+// One lane of a CONVERGED warp (elect.sync).  The MMA warp runs its loop with all 32 lanes on warp-uniform values and
+// issues tcgen05.mma / tcgen05.commit under this predicate: inside an `if (lane == 0)` region the compiler cannot use
+// the uniform datapath and rebuilds every descriptor operand with an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per MMA
+// -- ~87 cycles of issue per 64-cycle MMA (tools/mma_floor2.cu, profiles/r2_mma_floor2.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// fp32 -> (hi, lo): hi = nearest tf32 of v, lo = nearest tf32 of the (exact) remainder v - hi.  The tensor core
+// TRUNCATES fp32 operands to tf32; an unrounded remainder would lose up to 2^-22 |v| in one direction on every
+// element -- a bias that adds up linearly over K and put the 3xTF32 GEMM at ~1e-6 relative where fp32 FMA is at
+// 3e-7 (tests/arbiter.py).  Rounded, the error per operand is 2^-24 |v| with either sign.
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
-  uint32_t h;
+  uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
   hi = __uint_as_float(h);
-  lo = v - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
 }
 
 }  // namespace sm100

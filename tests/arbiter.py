@@ -7,6 +7,16 @@ multiple of the fp32 oracle's own distance to fp64:
 
         err(ours, fp64)  <=  FACTOR * err(oracle_fp32, fp64) + FLOOR
 
+For GRADIENTS at sizes with millions of ReLU / max-pool kinks that bound alone is not meaningful: a forward that is
+inside the spec (1e-5 relative, BASELINE.json north_star) flips the masks of the pre-activations lying within its
+error of zero, each flip changes one gradient element by O(1), and the relative L2 error is ~sqrt(flips / elements)
+-- torch CPU fp32 (3e-7 forward error) happens to flip none at these sizes, a 3xTF32 tensor-core forward (1e-6 ... 7e-6,
+the tensor core accumulates with truncation) flips tens.  The allowance for that is not fitted to our error either:
+it is MEASURED on the float64 model as the gradient change caused by a forward perturbation of exactly the size
+the spec allows (`Perturb`: every BatchNorm output + 1e-5 * max|output| * random sign) -- the "spec budget".
+
+        err(ours, fp64)  <=  max(FACTOR * err(oracle_fp32, fp64), budget) + FLOOR
+
 The discrete decisions (FPS order, ball-query / 3-NN indices, and the 3-NN distances the weights are built from)
 are taken from the fp32 oracle kernels -- they are integer outputs that all three sides share bit for bit -- so
 the fp64 computation is the exact-arithmetic version of the SAME function: grouping by those indices, centre
@@ -97,6 +107,65 @@ def backbone_forward64(bb64, O, cloud):
 def to64(module):
     """Deep copy of an oracle module in float64 (same parameters, same BatchNorm buffers)."""
     return copy.deepcopy(module).double()
+
+
+class Perturb:
+    """Context manager: while active, every BatchNorm output of `modules` (float64 oracle modules) is shifted by
+    eps * max|output| * (random sign) -- a forward error of exactly the size the spec tolerates.  The gradient change
+    it causes is the budget a spec-compliant implementation may use."""
+
+    def __init__(self, modules, eps=1e-5, seed=1234):
+        self.modules = modules if isinstance(modules, (list, tuple)) else [modules]
+        self.eps, self.gen, self.handles = eps, torch.Generator().manual_seed(seed), []
+
+    def _hook(self, _mod, _inp, out):
+        sign = torch.randint(0, 2, out.shape, generator=self.gen, dtype=torch.int8).to(out.dtype) * 2 - 1
+        return out + self.eps * out.detach().abs().max() * sign
+
+    def __enter__(self):
+        for m in self.modules:
+            for sub in m.modules():
+                if isinstance(sub, torch.nn.modules.batchnorm._BatchNorm):
+                    self.handles.append(sub.register_forward_hook(self._hook))
+        return self
+
+    def __exit__(self, *exc):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+
+def arbitrate(tag, ours, oracle32, run64, modules64, factor=FACTOR, floor=FLOOR):
+    """ours / oracle32: dicts name -> tensor (outputs and gradients).  run64(): evaluates the float64 model and returns
+    the same dict; it is called twice, plain and under `Perturb`.  Raises with a table if any quantity is out of bounds."""
+    exact = run64()
+    with Perturb(modules64):
+        pert = run64()
+    rep = Report(tag)
+    for k in ours:
+        rep.check(k, ours[k], oracle32[k], exact[k], factor=factor, floor=floor, budget=rel_l2(pert[k], exact[k]))
+    return rep.assert_ok()
+
+
+class Report:
+    """Collects every arbitrated quantity of a test and fails once, listing all of them (so a failing run shows the
+    whole picture, not the first violation)."""
+
+    def __init__(self, tag=""):
+        self.tag, self.rows = tag, []
+
+    def check(self, name, ours, oracle32, exact64, factor=FACTOR, floor=FLOOR, metric=rel_l2, budget=0.0):
+        e_ours, e_ref = metric(ours, exact64), metric(oracle32, exact64)
+        self.rows.append((name, e_ours, e_ref, e_ours <= max(factor * e_ref, budget) + floor, budget, floor))
+        return e_ours, e_ref
+
+    def assert_ok(self):
+        bad = [r for r in self.rows if not r[3]]
+        worst = sorted(self.rows, key=lambda r: -(r[1] / max(r[2], 1e-300)))[:8]
+        lines = [f"{n}: |ours-fp64| {a:.3e}  |oracle32-fp64| {b:.3e}  spec budget {bud:.3e}  {'ok' if ok else 'VIOLATION'}"
+                 for n, a, b, ok, bud, _ in (bad + worst)]
+        assert not bad, f"{self.tag}: {len(bad)} of {len(self.rows)} arbitrated quantities out of bounds\n" + "\n".join(lines)
+        return worst
 
 
 def check(name, ours, oracle32, exact64, factor=FACTOR, floor=FLOOR, metric=rel_l2):

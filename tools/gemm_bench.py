@@ -29,6 +29,8 @@ def timeit(fn, iters=10, warm=2):
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     shapes = SHAPES[:1] if "--one" in sys.argv else SHAPES
+    if os.environ.get("PN2_BENCH_SHAPE"):
+        shapes = [SHAPES[int(os.environ["PN2_BENCH_SHAPE"])]]
     dev = "cuda"
     for rows, k, n in shapes:
         yprev = torch.randn(rows, k, device=dev)
