@@ -157,6 +157,19 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity
   }
 }
 
+// the same for the hot loops: two instructions when the phase is already complete (the guarded form above costs ~10),
+// a spin counter that traps after ~2^26 timed-out tries instead of the clock arithmetic
+__device__ __forceinline__ void mbar_wait_fast(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+      "W%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D%=;\n\t"
+      "add.u32 n, n, 1;\n\tsetp.gt.u32 p, n, 0x4000000;\n\t@p trap;\n\tbra W%=;\n\t"
+      "D%=:\n\t}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -572,9 +585,9 @@ struct AsCfg {
   static constexpr bool kArg = AKIND == PN2_ROWS_DYPOOL;
   static constexpr bool kCoef = !(AKIND == PN2_ROWS_PLAIN || AKIND == PN2_ROWS_GATHER);
   static constexpr int kRawBytes = TILE_BYTES * (kDz ? 2 : 1) + (kArg ? AS_ARG_BYTES : 0);
-  static constexpr int kNR = kDz ? 3 : (kCoef ? 4 : 5);  // raw stages
+  static constexpr int kNR = kDz ? 3 : 5;                // raw stages
   static constexpr int kNB = kDz ? 3 : 4;                // weight stages
-  static constexpr int kCoefK = kCoef ? TC_KMAX : 0;     // largest K with per-channel coefficient vectors
+  static constexpr int kCoefK = kCoef ? 640 : 0;         // largest K with per-channel coefficient vectors (else FFMA kernel)
   static constexpr int kRing = kNB * BK_B_BYTES + kNR * kRawBytes;
   static constexpr int kSmem = kRing + 1024 /*align*/ + 512 /*barriers, tickets*/ + 3 * kCoefK * 4;
   static_assert(kSmem + 4096 /*static: statistics partials*/ <= 232448, "shared memory budget");
@@ -593,7 +606,7 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ float4 lds4(const unsigned char *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// what the ISSUING thread needs of a row: where it lives
+// what the ISSUING thread needs of a row: where it lives (element offsets, resolved once per tile)
 struct IssueCtx {
   bool valid;
   size_t off, goff;
@@ -638,7 +651,7 @@ __device__ __forceinline__ ConsCtx cons_ctx(const pn2_rows &s, int row, bool wan
 }
 
 template <int AKIND, int EPI>
-__global__ void __launch_bounds__(AS_CTA_THREADS, 1)
+__global__ void __launch_bounds__(AS_CTA_THREADS, 1)  // 96 registers: more (__maxnreg__ 104 / 112) does not launch with 18 warps
 gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   using Cfg = AsCfg<AKIND>;
   constexpr int NR = Cfg::kNR, NB = Cfg::kNB, NA = AS_NA;
@@ -662,14 +675,18 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   const int ntn = (g.N + TN - 1) / TN;
   const int ntiles = ((g.M + TM - 1) / TM) * ntn;
   const int num_kb = (g.K + TK - 1) / TK;
-  const int last_ticket = ntiles + 5 * static_cast<int>(gridDim.x) - 1;  // every CTA draws exactly five tickets past the end
+  // Tile tickets: the first five of every CTA are STATIC (blockIdx + i * grid -- drawn dynamically up front, the CTAs that
+  // start first would take five tiles each and leave late starters with none), the later ones come from the global
+  // counter (values 5 * grid + k).  Every CTA draws once per tile it processes, so exactly `ntiles` dynamic draws are
+  // made per launch and the one that returns ntiles - 1 resets the counter for the next launch that uses this slot.
+  const int grid_n = static_cast<int>(gridDim.x);
   trace_stamp(g, blockIdx.x, 0, smid());
   trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
 
   auto draw = [&]() {  // thread 0
-    const int t = atomicAdd(g.tile_counter, 1);
-    if (t == last_ticket) *g.tile_counter = 0;  // the last draw of the whole grid: nobody draws again
-    return t;
+    const int k = atomicAdd(g.tile_counter, 1);
+    if (k == ntiles - 1) *g.tile_counter = 0;
+    return 5 * grid_n + k;
   };
   if (tid == 0) {
     for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
@@ -679,12 +696,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
     mbar_init(tile_bar, 1);
     mbar_fence_init();
     fence_proxy_async_smem();  // the initialised barriers must be visible to the async proxy (bulk-copy complete_tx)
-    int t[5];
-    for (int i = 0; i < 5; ++i) t[i] = atomicAdd(g.tile_counter, 1);  // five independent atomics in flight together
-    for (int i = 0; i < 5; ++i) {
-      if (t[i] == last_ticket) *g.tile_counter = 0;
-      ticket[i] = t[i];
-    }
+    for (int i = 0; i < 5; ++i) ticket[i] = static_cast<int>(blockIdx.x) + i * grid_n;
   }
   if (warp == 0) tmem_alloc<AS_TMEM_COLS>(tmem_slot);
   if (producer && Cfg::kCoef) stage_coef<AKIND>(g.A, coef_a, Cfg::kCoefK, 0, min(g.K, Cfg::kCoefK), tid);
@@ -795,18 +807,19 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
       if (i_lr) mbar_wait_guarded(&raw_empty[i_sr], i_pr ^ 1);
       const uint32_t raw = ring_r_s + i_sr * Cfg::kRawBytes;
       const int c4 = kb * TK + chunk * 4;
+      const bool col_ok = c4 < (AKIND == PN2_ROWS_GATHER ? g.A.feat_cols : g.A.cols);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        bool ok = c[i].valid && c4 < g.A.cols;
-        if (AKIND == PN2_ROWS_GATHER) ok = ok && c4 < g.A.feat_cols;
-        cp_async16(raw + ioff[i], ok ? static_cast<const void *>(g.A.x + c[i].off + c4) : dummy, ok ? 16 : 0);
+        const bool ok = c[i].valid && col_ok;
+        const int nb = ok ? 16 : 0;
+        cp_async16(raw + ioff[i], ok ? static_cast<const void *>(g.A.x + c[i].off + c4) : dummy, nb);
         if (Cfg::kDz) {
-          const float *dz = g.A.dz + (AKIND == PN2_ROWS_DYPOOL ? c[i].goff : c[i].off) + c4;
-          cp_async16(raw + TILE_BYTES + ioff[i], ok ? static_cast<const void *>(dz) : dummy, ok ? 16 : 0);
+          const size_t doff = (AKIND == PN2_ROWS_DYPOOL ? c[i].goff : c[i].off) + c4;
+          cp_async16(raw + TILE_BYTES + ioff[i], ok ? static_cast<const void *>(g.A.dz + doff) : dummy, nb);
+          if (Cfg::kArg)
+            cp_async4(raw + 2 * TILE_BYTES + (chunk * TM + rsub + 64 * i) * 4, ok ? static_cast<const void *>(g.A.arg + doff) : dummy,
+                      ok ? 4 : 0);
         }
-        if (Cfg::kArg)
-          cp_async4(raw + 2 * TILE_BYTES + (chunk * TM + rsub + 64 * i) * 4,
-                    ok ? static_cast<const void *>(g.A.arg + c[i].goff + c4) : dummy, ok ? 4 : 0);
       }
       cp_async_arrive(&raw_full[i_sr]);
       if (++i_sr == NR) { i_sr = 0; i_pr ^= 1; i_lr = 1; }
@@ -1010,6 +1023,7 @@ bool gemm_tc_enabled() {
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
+  if (akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER && g.K > 640) return PN2_TC_UNSUPPORTED;  // coefficient staging
   // PN2_TC_BULK=0 keeps every operand thread-staged (gemm_tc_kernel) for A/B measurements
   static const bool bulk_on = [] {
     const char *e = getenv("PN2_TC_BULK");
