@@ -284,7 +284,9 @@ def main_ours(args):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)  # NCCL_DEBUG is left to the caller: fd 1 already points at stderr
+        import datetime
+        # NCCL_DEBUG is left to the caller (fd 1 already points at stderr); a collective that hangs aborts after 3 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         group = dist.group.WORLD
     import _pn2
     from graphed import GraphedTrainStep

@@ -1,21 +1,19 @@
 """Whole-step CUDA graphs for models built on the fused PointNet++ path.
 
 A backbone forward+backward is ~150 short kernels on two streams; launched from Python the host needs longer to
-enqueue them than the GPU needs to run them (bench.py --no-graph: 9.3 vs 3.9 ms per scene).  `GraphedTrainStep`
-captures ONE CUDA graph that holds
+enqueue them than the GPU needs to run them (bench.py --no-graph: 9.3 vs 3.7 ms per scene).  `GraphedTrainStep`
+captures ONE CUDA graph that holds   forward -> loss -> backward   and replays it per step; with a process group
+the replay is followed by ONE NCCL all-reduce (ReduceOp.AVG) of the whole gradient arena.  It replaces, for the part of
+train.py that drives the path (`end_points = model(inputs)` ... `loss.backward()` under DistributedDataParallel,
+train.py:382,486-520):
 
-    forward  ->  loss  ->  backward  ->  gradient all-reduce over NCCL (when a process group is given)
-
-and replays it per step.  It replaces, for the part of train.py that drives the path
-(`end_points = model(inputs)` ... `loss.backward()` under DistributedDataParallel, train.py:382,486-520):
-
-  * torch.cuda.make_graphed_callables + DistributedDataParallel: there the whole backward is one autograd node,
-    so DDP's bucket hooks fire only after the last backward kernel and every step pays DDP's host-side bucket
-    bookkeeping plus an exposed ncclAllReduce between two graph replays (SCALE_r01: +0.4 ms flat at N >= 2);
+  * torch.cuda.make_graphed_callables + DistributedDataParallel (round 1): there every step paid DDP's host-side
+    bucket bookkeeping and hooks around two graph replays (SCALE_r01: +0.4 ms flat at N >= 2);
   * DDP's gradient buckets: parameter gradients are *produced in place* in one flat arena (`grad_slot`): the fused
     backward's weight-gradient kernels write straight into their slice, AccumulateGrad adopts the slice as
-    `param.grad`, and the arena is all-reduced (ReduceOp.AVG, like DDP) in a few large pieces on a communication
-    stream that forks off the capture as soon as the pieces' last gradient exists -- inside the same graph.
+    `param.grad`, and the arena is reduced in one call -- no per-parameter copies into buckets, no hooks.
+    (Capturing the all-reduce INSIDE the graph, issued from gradient hooks on a forked stream, was tried and hung at
+    N = 2 on the first attempt; it is not in the tree.)
 
 Semantics kept: after `step(inputs)` every `param.grad` holds the rank-averaged gradient (DDP's contract,
 `broadcast_buffers=False` as in train.py:382: BatchNorm running statistics are per rank), the returned loss is
@@ -38,10 +36,9 @@ def grad_slot(param):
 
 
 class _Arena:
-    """One flat fp32 buffer holding every trainable parameter's gradient, laid out in REVERSE registration order
-    (the order backward produces them in), cut into `pieces` for the all-reduce."""
+    """One flat fp32 buffer holding every trainable parameter's gradient (16-byte aligned slices)."""
 
-    def __init__(self, params, piece_bytes):
+    def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         order = list(reversed(self.params))
         offs, total = [], 0
@@ -51,17 +48,8 @@ class _Arena:
         dev = order[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.slots = {}
-        self.pieces = []  # (start, end, [params])
-        start, members = 0, []
         for p, off in zip(order, offs):
             self.slots[p] = self.flat[off:off + p.numel()].view_as(p)
-            members.append(p)
-            end = off + (p.numel() + 3) // 4 * 4
-            if (end - start) * 4 >= piece_bytes:
-                self.pieces.append((start, end, members))
-                start, members = end, []
-        if members:
-            self.pieces.append((start, total, members))
 
     def attach(self):
         for p, s in self.slots.items():
@@ -74,7 +62,7 @@ class _Arena:
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, sample_inputs, process_group=None, piece_bytes=4 << 20, warmup=3):
+    def __init__(self, model, loss_fn, sample_inputs, process_group=None, warmup=3):
         """model: nn.Module; loss_fn(model_output) -> scalar tensor; sample_inputs: tuple of CUDA tensors with the
         shapes every later call will use; process_group: None (single rank) or a NCCL group to average gradients over."""
         if not isinstance(sample_inputs, (tuple, list)):
@@ -83,79 +71,42 @@ class GraphedTrainStep:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if process_group is not None else 1
         self.static_in = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in sample_inputs)
-        self.arena = _Arena(list(model.parameters()), piece_bytes)
+        self.arena = _Arena(list(model.parameters()))
         dev = self.static_in[0].device
-        self.comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.launches_per_step = None
 
         self.arena.attach()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # warm-up outside the capture: allocator pools, lazy module state, NCCL communicator
+        with torch.cuda.stream(side):  # warm-up outside the capture: allocator pools, lazy module state
             for _ in range(warmup):
-                self._run(capturing=False)
+                self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         import _pn2
         before = _pn2.kernel_launches()
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._run(capturing=True)
+            self.static_loss = self._run()
         self.launches_per_step = _pn2.kernel_launches() - before
         self.arena.detach()  # the graph holds the pointers; eager calls of the model afterwards behave normally
 
-    # one forward + backward (+ all-reduce); gradients end up in the arena
-    def _run(self, capturing):
+    # one forward + backward; gradients end up in the arena
+    def _run(self):
         for p in self.arena.params:
             p.grad = None
         for t in self.static_in:
             t.grad = None
-        pending = {id(piece): len(piece[2]) for piece in self.arena.pieces}
-        owner = {}
-        for piece in self.arena.pieces:
-            for p in piece[2]:
-                owner[p] = piece
-        handles = []
-        main = torch.cuda.current_stream()
-        launched = []
-
-        def reduce_piece(piece):
-            if self.world <= 1:
-                return
-            start, end, _ = piece
-            self.comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.comm):
-                dist.all_reduce(self.arena.flat[start:end], op=dist.ReduceOp.AVG, group=self.group)
-            launched.append(piece)
-
-        def on_grad(p):
-            slot = self.arena.slots[p]
-            if p.grad is not None and p.grad.data_ptr() != slot.data_ptr():
-                slot.copy_(p.grad)  # a gradient produced outside the fused path: move it into the arena
-                p.grad = slot
-            piece = owner[p]
-            pending[id(piece)] -= 1
-            if pending[id(piece)] == 0:
-                reduce_piece(piece)
-
+        out = self.model(*self.static_in)
+        loss = self.loss_fn(out)
+        loss.backward()
         for p in self.arena.params:
-            handles.append(p.register_post_accumulate_grad_hook(on_grad))
-        try:
-            out = self.model(*self.static_in)
-            loss = self.loss_fn(out)
-            loss.backward()
-        finally:
-            for h in handles:
-                h.remove()
-        for piece in self.arena.pieces:  # parameters that received no gradient this step: reduce what is there
-            if pending[id(piece)] > 0 and piece not in launched:
-                for p in piece[2]:
-                    if p.grad is None:
-                        self.arena.slots[p].zero_()
-                        p.grad = self.arena.slots[p]
-                reduce_piece(piece)
-        if self.comm is not None:
-            main.wait_stream(self.comm)  # join the communication stream back into the capture
+            slot = self.arena.slots[p]
+            if p.grad is None:
+                slot.zero_()  # no gradient this step (unused parameter): contributes zero to the average
+            elif p.grad.data_ptr() != slot.data_ptr():
+                slot.copy_(p.grad)  # a gradient produced outside the fused path: move it into the arena
+            p.grad = slot
         return loss.detach()
 
     def __call__(self, *inputs):
@@ -163,6 +114,8 @@ class GraphedTrainStep:
             for dst, src in zip(self.static_in, inputs):
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        if self.world > 1:  # DDP's contract: every rank ends up with the average gradient
+            dist.all_reduce(self.arena.flat, op=dist.ReduceOp.AVG, group=self.group)
         for p, slot in self.arena.slots.items():  # an eager step in between may have re-pointed .grad
             p.grad = slot
         return self.static_loss

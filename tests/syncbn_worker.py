@@ -26,8 +26,11 @@ def rel(a, b):
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(0)
-    dist.init_process_group("gloo")
+    backend = os.environ.get("PN2_SYNCBN_BACKEND", "gloo")
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if backend == "nccl" else 0  # nccl: one GPU per rank; gloo: both on cuda:0
+    torch.cuda.set_device(dev)
+    import datetime
+    dist.init_process_group(backend, timeout=datetime.timedelta(seconds=120))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     import pointnet2_modules as M
@@ -54,8 +57,8 @@ def main():
     ours = torch.nn.SyncBatchNorm.convert_sync_batchnorm(ours).cuda().train()
     theirs = torch.nn.SyncBatchNorm.convert_sync_batchnorm(theirs).cuda().train()
     assert isinstance(ours.sa.mlp_module.layer0.bn.bn, torch.nn.SyncBatchNorm)
-    d_ours = DDP(ours, device_ids=[0], broadcast_buffers=False)
-    d_theirs = DDP(theirs, device_ids=[0], broadcast_buffers=False)
+    d_ours = DDP(ours, device_ids=[dev], broadcast_buffers=False)
+    d_theirs = DDP(theirs, device_ids=[dev], broadcast_buffers=False)
 
     n = [500, 500][rank]
     b = [2, 3][rank]  # ranks hold different numbers of rows: the global count matters

@@ -3,7 +3,7 @@
 # Writes (all small enough to be merged back): gpurun_out/<tag>_launches.csv  (every launch, gpu__time_duration),
 # <tag>_gemm_raw.csv / <tag>_rest_raw.csv (ncu --set full, --page raw).
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ref-gpu --no-graph"

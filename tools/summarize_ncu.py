@@ -74,6 +74,14 @@ def main():
             per[key].append(r.get("dram__bytes_read.sum_bytes", 0) + r.get("dram__bytes_write.sum_bytes", 0))
         for k, v in per.items():
             traffic[k] = sum(v) / len(v)
+        if part == "gemm":  # the capture holds exactly one step's GEMM launches (tools/profile_step.sh)
+            traffic["gemm_launches_captured"] = len(rows)
+            traffic["gemm_dram_bytes_per_step"] = sum(r.get("dram__bytes_read.sum_bytes", 0) + r.get("dram__bytes_write.sum_bytes", 0)
+                                                      for r in rows)
+            traffic["gemm_us_per_step_under_ncu"] = sum(float(r["gpu__time_duration.sum"].replace(",", "")) for r in rows)
+            tp = [float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"].replace(",", "")) for r in rows]
+            tt = [float(r["gpu__time_duration.sum"].replace(",", "")) for r in rows]
+            traffic["gemm_tensor_pipe_active_pct_time_weighted"] = sum(a * b for a, b in zip(tp, tt)) / max(sum(tt), 1e-9)
     if traffic:
         json.dump(traffic, open(os.path.join(p, f"{tag}_ncu_traffic.json"), "w"), indent=1)
     lpath = os.path.join(g, f"{tag}_launches.csv")
