@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying "
                     "the step as one CUDA graph (graphed.GraphedTrainStep)")
+    ap.add_argument("--no-prefetch", action="store_true", help="compute the first level's FPS + ball query inside the step "
+                    "instead of one step ahead on a side stream")
     ap.add_argument("--extras", action="store_true", help="also measure configs[3] (8 clouds per rank) and configs[4] "
                     "(50k-point FP stress) sub-records at N=1 (always on for N>1)")
     return ap.parse_args()
@@ -315,7 +317,9 @@ def main_ours(args):
 
     step, graph_check = None, None
     if not args.no_graph:
-        step = GraphedTrainStep(net, lambda out: out.sum(), (batch_of(resident, 0),), process_group=group)
+        # level-1 geometry of the NEXT batch runs underneath the current step (a training loop knows its next batch)
+        step = GraphedTrainStep(net, lambda out: out.sum(), (batch_of(resident, 0),), process_group=group,
+                                prefetch=None if args.no_prefetch else (model.sa1, lambda inp: inp[0][..., :3]))
         if world == 1:  # (with N > 1 the replay holds rank-averaged gradients, the eager step this rank's)
             graph_check = check_graph_against_eager(model, net, step, batch_of(resident, 1), params)
             assert graph_check["ok"], f"graph replay differs from the eager step: {graph_check}"
@@ -329,13 +333,28 @@ def main_ours(args):
                 dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         return loss
 
-    run = step if step is not None else eager_step
+    prefetching = step is not None and not args.no_prefetch
+    seq = [0]  # running batch number: warm-up and timed loops continue one sequence, so an announced next batch follows
 
-    def step_resident(it):
-        run(batch_of(resident, it))
+    def step_resident(_it):
+        it = seq[0]
+        seq[0] += 1
+        if prefetching:
+            step(batch_of(resident, it), next_inputs=(batch_of(resident, it + 1),))
+        elif step is not None:
+            step(batch_of(resident, it))
+        else:
+            eager_step(batch_of(resident, it))
 
-    def step_e2e(it):
-        loss = run(batch_of(host, it).to(dev, non_blocking=True) if step is None else batch_of(host, it))
+    def step_e2e(_it):
+        it = seq[0]
+        seq[0] += 1
+        if prefetching:  # this step's cloud was announced by the previous call and copied from pinned host memory then
+            loss = step(batch_of(host, it), next_inputs=(batch_of(host, it + 1),))
+        elif step is not None:
+            loss = step(batch_of(host, it))
+        else:
+            loss = eager_step(batch_of(host, it).to(dev, non_blocking=True))
         return float(loss.item())  # D2H of the step's result
 
     for it in range(max(args.warmup, 3)):
@@ -428,7 +447,8 @@ def main_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload(args), cuda_graph=step is not None, backbone=backbone_src),
+                "config": dict(workload(args), cuda_graph=step is not None, backbone=backbone_src,
+                               geometry_prefetch=prefetching),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": args.batch * args.points * 6 * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

@@ -533,7 +533,10 @@ __device__ int g_tile_counters[1024];
 inline int persistent_spare() {
   static const int spare = [] {
     const char *e = getenv("PN2_TC_PERSISTENT_SPARE");
-    return e ? atoi(e) : 8;  // measured: 0 -> 4.11, 8 -> 3.92, 16 -> 3.93 ms per step (profiles/r1_bench_*spare*)
+    // round 1 (geometry inside the step): 0 -> 4.11, 8 -> 3.92, 16 -> 3.93 ms per step.  Round 2, with the next batch's
+    // level-1 FPS (one 16-CTA cluster) prefetched underneath the step: 8 -> 3.24, 16 -> 3.09, 24 -> 3.27 ms
+    // (profiles/r2_bench_spare*.json): the cluster needs 16 SMs free at the same time
+    return e ? atoi(e) : 16;
   }();
   return spare;
 }

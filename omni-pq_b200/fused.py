@@ -262,7 +262,12 @@ class _SAFunction(torch.autograd.Function):
                 feat_pm_, ldf_ = None, 0
             return feat_pm_, ldf_, _prep_layers(layers, ldf_ + (4 if use_xyz else 0), 1 if use_xyz else 0, ldf_)
 
-        if _SIDE_STREAM and (_SIDE_IN_GRAPH or not torch.cuda.is_current_stream_capturing()):
+        pre = getattr(module, "_pn2_geom", None)  # geometry computed ahead of the step (graphed.GraphedTrainStep prefetch)
+        if pre is not None and inds is None and tuple(pre[0].shape) == (b, n, 3) and tuple(pre[3].shape) == (b, m, ns):
+            # fresh views: the static buffers themselves must not pick up this call's autograd history
+            xyz_c, inds, new_xyz, idx = (t.view(t.shape) for t in pre)
+            feat_pm, ldf, state = activation_independent()
+        elif _SIDE_STREAM and (_SIDE_IN_GRAPH or not torch.cuda.is_current_stream_capturing()):
             main, side = torch.cuda.current_stream(xyz.device), _geom_stream(xyz.device)
             if not xyz_on_side or inds is not None:
                 side.wait_stream(main)  # coordinates (or given indices) were produced on the MLP stream
@@ -340,9 +345,20 @@ def sa_forward(module, xyz, features, inds):
         new_xyz, out, inds, out_pm = _SAFunction.apply(module, layers, _cached_pm(features), on_side, xyz, features, inds,
                                                        *_flat_params(layers))
     _remember_pm(out, out_pm)
-    if _SIDE_STREAM:
+    if _SIDE_STREAM and getattr(module, "_pn2_geom", None) is None:
         new_xyz._pn2_side = (new_xyz._version, tuple(new_xyz.shape))  # produced on the geometry stream
     return new_xyz, out, inds
+
+
+def sa_geometry(module, xyz):
+    """The coordinate-only part of a set-abstraction level -- FPS (+ centre gather) and the ball query -- as
+    (xyz contiguous, inds, new_xyz, idx).  It depends on the cloud alone, so a training loop that knows its NEXT batch
+    can run it underneath the current step (graphed.GraphedTrainStep(prefetch=...)); the module consumes the result
+    through `module._pn2_geom`."""
+    with torch.cuda.device(xyz.device):
+        xyz_c = xyz.detach().contiguous()
+        inds, new_xyz = K.furthest_point_sampling(xyz_c, module.npoint, return_xyz=True)
+        return xyz_c, inds, new_xyz, K.ball_query(new_xyz, xyz_c, module.radius, module.nsample)
 
 
 # ---- feature propagation -----------------------------------------------------------------------------------

@@ -24,6 +24,18 @@ fresh tensors every step.
     loss = step(cloud)              # tensors in, 0-dim loss tensor out (static buffer: read it before the next step)
     optimizer.step()                # param.grad tensors are stable views into the arena
 
+Geometry prefetch: the first set-abstraction level's FPS + ball query depend on
+the cloud alone and are the one part of the step nothing else can hide (0.9 ms of 3.7 at batch 1: a 2047-round
+dependent arg-max chain on one 16-SM cluster).  A training loop knows its next batch (the reference prefetches with
+DataLoader workers, train.py:257-262), so
+
+    step = GraphedTrainStep(model, loss_fn, sample, prefetch=(model.backbone.sa1, lambda inputs: inputs[0][..., :3]))
+    loss = step(cloud_t, next_inputs=(cloud_t1,))      # ... and the following call must be step(cloud_t1, ...)
+
+copies the NEXT batch (host or device) and runs its level-1 geometry as a second small graph on a side stream
+underneath the current step's MLPs and backward; the next call finds indices and centres ready.  Every step still
+computes its own geometry exactly once, with the same kernels -- only the schedule changes, results are identical.
+
 `GraphedForward` is the inference counterpart (teacher / EMA forward under no_grad, train.py:490-491, and eval).
 """
 import torch
@@ -62,9 +74,11 @@ class _Arena:
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, sample_inputs, process_group=None, warmup=3):
+    def __init__(self, model, loss_fn, sample_inputs, process_group=None, warmup=3, prefetch=None):
         """model: nn.Module; loss_fn(model_output) -> scalar tensor; sample_inputs: tuple of CUDA tensors with the
-        shapes every later call will use; process_group: None (single rank) or a NCCL group to average gradients over."""
+        shapes every later call will use; process_group: None (single rank) or a NCCL group to average gradients over;
+        prefetch: None or (sa_module, xyz_of) -- the set-abstraction module whose geometry is computed one step ahead and
+        a function mapping the input tuple to its (B, N, 3) coordinates."""
         if not isinstance(sample_inputs, (tuple, list)):
             sample_inputs = (sample_inputs,)
         self.model, self.loss_fn = model, loss_fn
@@ -74,6 +88,29 @@ class GraphedTrainStep:
         self.arena = _Arena(list(model.parameters()))
         dev = self.static_in[0].device
         self.launches_per_step = None
+        self.prefetch = prefetch
+        if prefetch is not None:
+            import fused
+            sa, xyz_of = prefetch
+            self.static_next = tuple(t.detach().clone() for t in sample_inputs)  # the batch the geometry graph works on
+            self.geom_stream = torch.cuda.Stream(device=dev)
+            self.geom_done, self.consumed = torch.cuda.Event(), torch.cuda.Event()
+            self.next_ready = False
+            warm = torch.cuda.Stream(device=dev)
+            warm.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(warm):
+                fused.sa_geometry(sa, xyz_of(self.static_next))
+            torch.cuda.current_stream(dev).wait_stream(warm)
+            torch.cuda.synchronize(dev)
+            self.geom_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.geom_graph):
+                self.geom_next = fused.sa_geometry(sa, xyz_of(self.static_next))
+            self.geom_graph.replay()
+            torch.cuda.synchronize(dev)
+            self.geom_cur = tuple(t.clone() for t in self.geom_next)  # what the main graph reads
+            for dst, src in zip(self.static_in, self.static_next):
+                dst.detach().copy_(src)
+            sa._pn2_geom = self.geom_cur
 
         self.arena.attach()
         side = torch.cuda.Stream(device=dev)
@@ -90,6 +127,9 @@ class GraphedTrainStep:
             self.static_loss = self._run()
         self.launches_per_step = _pn2.kernel_launches() - before
         self.arena.detach()  # the graph holds the pointers; eager calls of the model afterwards behave normally
+        if prefetch is not None:
+            del prefetch[0]._pn2_geom
+            self.launches_per_step += 2  # FPS + ball query of the prefetched level run in the geometry graph
 
     # one forward + backward; gradients end up in the arena
     def _run(self):
@@ -109,11 +149,36 @@ class GraphedTrainStep:
             p.grad = slot
         return loss.detach()
 
-    def __call__(self, *inputs):
+    def __call__(self, *inputs, next_inputs=None):
+        """One training step on `inputs`.  With prefetch: pass the FOLLOWING batch as `next_inputs` (device or pinned
+        host tensors); the next call must then be made with exactly that batch."""
+        main = torch.cuda.current_stream(self.static_in[0].device)
         with torch.no_grad():
-            for dst, src in zip(self.static_in, inputs):
-                dst.copy_(src, non_blocking=True)
+            if self.prefetch is None:
+                for dst, src in zip(self.static_in, inputs):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                if self.next_ready:
+                    main.wait_event(self.geom_done)  # batch + geometry staged under the previous step (or a stale prefetch)
+                staged = self.next_ready and all(a.data_ptr() == b.data_ptr() and a.shape == b.shape
+                                                 for a, b in zip(inputs, self._next_ref))
+                if not staged:  # first call, or the caller did not continue with the batch it announced
+                    for dst, src in zip(self.static_next, inputs):
+                        dst.copy_(src, non_blocking=True)
+                    self.geom_graph.replay()
+                torch._foreach_copy_([t.detach() for t in self.static_in], list(self.static_next))
+                torch._foreach_copy_(list(self.geom_cur), list(self.geom_next))
+                self.consumed.record(main)
+                self.next_ready = False
         self.graph.replay()
+        if self.prefetch is not None and next_inputs is not None:
+            with torch.no_grad(), torch.cuda.stream(self.geom_stream):
+                self.geom_stream.wait_event(self.consumed)  # the staging buffers were copied out
+                for dst, src in zip(self.static_next, next_inputs):
+                    dst.copy_(src, non_blocking=True)
+                self.geom_graph.replay()
+                self.geom_done.record(self.geom_stream)
+            self.next_ready, self._next_ref = True, tuple(next_inputs)
         if self.world > 1:  # DDP's contract: every rank ends up with the average gradient
             dist.all_reduce(self.arena.flat, op=dist.ReduceOp.AVG, group=self.group)
         for p, slot in self.arena.slots.items():  # an eager step in between may have re-pointed .grad

@@ -503,7 +503,8 @@ def test_fused_fp_three_nn_indices_bit_exact_under_ties(case, K, O):
 
 
 # ---- the timed path: whole-step CUDA graph == eager ----------------------------------------------------------------
-def test_graphed_train_step_matches_eager(K, O):
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_graphed_train_step_matches_eager(prefetch, K, O):
     """bench.py times graphed.GraphedTrainStep replays (forward + backward + the side-stream fork/join in ONE CUDA
     graph, gradients produced in the arena); every other parity test runs eagerly.  Over 4 replays with rotating
     inputs the replay must reproduce the eager step: the forward output and the BatchNorm buffers bit for bit (no atomics
@@ -533,14 +534,16 @@ def test_graphed_train_step_matches_eager(K, O):
         return (out * cot).sum()
 
     state0 = {k: v.clone() for k, v in model.state_dict().items()}
-    step = GraphedTrainStep(net, loss_fn, (scenes[0][None],))
+    # prefetch: the first level's FPS + ball query of the NEXT batch run on a side stream underneath the current step
+    step = GraphedTrainStep(net, loss_fn, (scenes[0][None],),
+                            prefetch=(model.sa1, lambda inp: inp[0][..., :3]) if prefetch else None)
     static_out = outs["last"]
     assert step.launches_per_step and step.launches_per_step > 50
     params = [p for p in model.parameters()]
     for it in range(4):
         cloud = scenes[it % 3][None]
         model.load_state_dict(state0)           # same BatchNorm running statistics on both sides
-        loss_g = step(cloud).clone()
+        loss_g = (step(cloud, next_inputs=(scenes[(it + 1) % 3][None],)) if prefetch else step(cloud)).clone()
         out_g = static_out.clone()
         grads_g = [p.grad.clone() for p in params]
         bufs_g = {k: v.clone() for k, v in model.state_dict().items()}
