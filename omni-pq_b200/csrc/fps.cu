@@ -5,14 +5,14 @@
 //
 // FPS is a chain of m-1 dependent arg-max rounds; its compulsory HBM traffic is 12*N + 4*m bytes,
 // so it is latency-bound, not bandwidth-bound.  Design (see DESIGN.md "FPS"):
-//   * one thread-block CLUSTER (1..16 CTAs of 128 threads) per cloud; every point lives in
+//   * one thread-block CLUSTER (1..16 CTAs of 512 threads) per cloud; every point lives in
 //     registers (x, y, z, running min-distance) for the whole kernel -> xyz is read from HBM once
 //     and the reference's temp[] scratch never exists;
-//   * per round: register update -> warp arg-max with redux.sync -> 4 warp candidates through
-//     shared memory (one bar.sync) -> CTA candidate pushed to every CTA of the cluster with
-//     st.async (DSMEM store that completes a transaction on the receiver's mbarrier) -> every warp
-//     reduces the <=16 CTA candidates; the candidate carries the winner's coordinates so the next
-//     round starts without another memory round trip;
+//   * per exchange round: register update -> warp arg-max with redux.sync -> the warps' candidates AND a bound on
+//     every other point through shared memory (one bar.sync) -> each CTA's two best candidates + its bound pushed to
+//     every CTA of the cluster with st.async (DSMEM store that completes a transaction on the receiver's mbarrier)
+//     -> every warp resolves as many picks as the bound proves exact (fps_multipick_kernel below, ~8 per round);
+//     candidates carry their coordinates so the next round starts without another memory round trip;
 //   * buffers are double-buffered on the round parity, which makes one barrier per level enough.
 //
 // Bit-exactness with the reference (index output):
@@ -204,132 +204,9 @@ __device__ __forceinline__ int warp_argmax_lane(int d, int k, bool active, int b
   return __ffs(__ballot_sync(0xffffffffu, r == rm)) - 1;
 }
 
-template <int NW>
-struct alignas(16) FpsSmem2 {
-  uint4 wcand[2][NW];             // per-warp candidate {d, k, x bits, y bits}
-  uint4 ccand[2][kFpsMaxCluster]; // per-CTA candidates received from the cluster
-  float wz[2][NW];
-  float cz[2][kFpsMaxCluster];
-  unsigned long long bar[2];
-};
-
-template <int PTS>
-__global__ void __launch_bounds__(kFpsThreads, 1)
-fps_resident_kernel(int n, int m, int cs, int bs_log2, const float *__restrict__ xyz,
-                    int *__restrict__ idxs, float *__restrict__ new_xyz) {
-  pdl_prologue();
-  constexpr int NW = kFpsThreads / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FpsSmem2<NW> &S = *reinterpret_cast<FpsSmem2<NW> *>(smem_raw);
-  float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem2<NW>));
-  float *sy = sx + PTS * kFpsThreads;
-  float *sz = sy + PTS * kFpsThreads;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t my_cta = cs > 1 ? cluster_ctarank() : 0u;
-  const int batch = blockIdx.x / cs;
-  xyz += static_cast<size_t>(batch) * n * 3;
-  idxs += static_cast<size_t>(batch) * m;
-  if (new_xyz) new_xyz += static_cast<size_t>(batch) * m * 3;
-  const int T = cs * kFpsThreads;
-  const int g = static_cast<int>(my_cta) * kFpsThreads + tid;
-
-  float px[PTS], py[PTS], pz[PTS], pt[PTS];
-#pragma unroll
-  for (int i = 0; i < PTS; ++i) {
-    const int k = g + i * T;
-    float x = 0.f, y = 0.f, z = 0.f;
-    bool valid = false;
-    if (k < n) {
-      x = xyz[k * 3 + 0];
-      y = xyz[k * 3 + 1];
-      z = xyz[k * 3 + 2];
-      valid = !(static_cast<double>(sq3(x, y, z)) <= 1e-3);  // sampling_gpu.cu:105-106
-    }
-    px[i] = x; py[i] = y; pz[i] = z;
-    pt[i] = valid ? 1e10f : -1.0f;  // -1: never a candidate, fminf keeps it at -1
-    sx[i * kFpsThreads + tid] = x;
-    sy[i * kFpsThreads + tid] = y;
-    sz[i * kFpsThreads + tid] = z;
-  }
-  const float x0 = xyz[0], y0 = xyz[1], z0 = xyz[2];
-  float x1 = x0, y1 = y0, z1 = z0;
-  if (g == 0) {
-    idxs[0] = 0;
-    if (new_xyz) { new_xyz[0] = x0; new_xyz[1] = y0; new_xyz[2] = z0; }
-  }
-  if (cs > 1) {
-    if (tid == 0) {
-      mbar_init(&S.bar[0], 1);
-      mbar_init(&S.bar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_arrive_expect_tx(&S.bar[0], cs * kCandBytes);
-      mbar_arrive_expect_tx(&S.bar[1], cs * kCandBytes);
-    }
-    cluster_sync_all();
-  }
-
-  for (int j = 1; j < m; ++j) {
-    const int p = j & 1;
-    float best = -2.0f;
-    int ib = 0;
-#pragma unroll
-    for (int i = 0; i < PTS; ++i) {
-      const float d = dist2(px[i], py[i], pz[i], x1, y1, z1);
-      const float t = fminf(d, pt[i]);
-      pt[i] = t;
-      if (t > best) { best = t; ib = i; }  // strict '>': the lowest i (= lowest rank in this thread) wins ties
-    }
-    // ---- warp level ----
-    const int bits = __float_as_int(best);
-    const int kmine = g + ib * T;
-    if (lane == warp_argmax_lane(bits, kmine, true, bs_log2)) {
-      const int slot = ib * kFpsThreads + tid;
-      S.wcand[p][warp] = make_uint4(static_cast<uint32_t>(bits), static_cast<uint32_t>(kmine), __float_as_uint(sx[slot]),
-                                    __float_as_uint(sy[slot]));
-      S.wz[p][warp] = sz[slot];
-    }
-    __syncthreads();
-    // ---- CTA level (every warp redundantly) ----
-    FpsCand c;
-    {
-      uint4 e = make_uint4(0u, 0u, 0u, 0u);
-      if (lane < NW) e = S.wcand[p][lane];
-      const int src = warp_argmax_lane(static_cast<int>(e.x), static_cast<int>(e.y), lane < NW, bs_log2);
-      const uint4 w = S.wcand[p][src];
-      c.d = static_cast<int>(w.x); c.k = static_cast<int>(w.y);
-      c.x = __uint_as_float(w.z); c.y = __uint_as_float(w.w); c.z = S.wz[p][src];
-    }
-    // ---- cluster level ----
-    if (cs > 1) {
-      if (warp == 0 && lane < cs) {
-        const uint32_t rbar = mapa_u32(smem_u32(&S.bar[p]), lane);
-        st_async_v4(mapa_u32(smem_u32(&S.ccand[p][my_cta]), lane), rbar, static_cast<uint32_t>(c.d),
-                    static_cast<uint32_t>(c.k), __float_as_uint(c.x), __float_as_uint(c.y));
-        st_async_b32(mapa_u32(smem_u32(&S.cz[p][my_cta]), lane), rbar, __float_as_uint(c.z));
-      }
-      mbar_wait(&S.bar[p], ((j - 1) >> 1) & 1);
-      if (tid == 0) mbar_arrive_expect_tx(&S.bar[p], cs * kCandBytes);  // re-arm for round j+2
-      uint4 e = make_uint4(0u, 0u, 0u, 0u);
-      if (lane < cs) e = S.ccand[p][lane];
-      const int src = warp_argmax_lane(static_cast<int>(e.x), static_cast<int>(e.y), lane < cs, bs_log2);
-      const uint4 w = S.ccand[p][src];
-      c.d = static_cast<int>(w.x); c.k = static_cast<int>(w.y);
-      c.x = __uint_as_float(w.z); c.y = __uint_as_float(w.w); c.z = S.cz[p][src];
-    }
-    if (c.d < 0) { c.k = 0; x1 = x0; y1 = y0; z1 = z0; }  // nothing was a candidate: reference yields index 0
-    else { x1 = c.x; y1 = c.y; z1 = c.z; }
-    if (g == 0) {
-      idxs[j] = c.k;
-      if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
-    }
-  }
-  if (cs > 1) cluster_sync_all();  // keep every CTA's shared memory alive until all DSMEM stores landed
-}
-
 // ---- register-resident kernel, several picks per exchange round ----------------------------------------------
-// The chain above pays one block + cluster exchange (~1300 cycles) per sampled point.  Most of those
-// exchanges are avoidable without changing a single output bit:
+// One block + cluster exchange per sampled point costs ~1300 cycles (the round's first kernel, 0.68 us per sample at 40k
+// points; removed).  Most of those exchanges are avoidable without changing a single output bit:
 //
 //   After a round, let C be a set of candidate points whose current min-distances are known to every warp
 //   (with coordinates), and let `bmax` bound the min-distance of every point NOT in C.  Min-distances only
@@ -746,29 +623,10 @@ int launch_multipick(int b, int n, int m, int cs, int bs_log2, const float *xyz,
   return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
 }
 
-// PN2_FPS_MULTIPICK=0 selects the one-pick-per-round kernel (A/B measurements)
-bool fps_multipick_enabled() {
-  static const bool on = [] {
-    const char *e = getenv("PN2_FPS_MULTIPICK");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
-
 template <int PTS>
 int launch_resident(int b, int n, int m, int cs, int bs_log2, const float *xyz, int *idxs, float *new_xyz,
                     const int *identity_flag, cudaStream_t stream) {
-  if (fps_multipick_enabled())
-    return launch_multipick<PTS>(b, n, m, cs, bs_log2, xyz, idxs, new_xyz, identity_flag, stream);
-  auto kernel = fps_resident_kernel<PTS>;
-  const size_t smem = sizeof(FpsSmem2<kFpsThreads / 32>) + size_t(3) * PTS * kFpsThreads * sizeof(float);
-  static thread_local int configured_dev = -1;
-  if (!configured_on(configured_dev)) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  }
-  void *args[] = {&n, &m, &cs, &bs_log2, &xyz, &idxs, &new_xyz};
-  return launch_cluster(kernel, b * cs, kFpsThreads, smem, cs, stream, args);
+  return launch_multipick<PTS>(b, n, m, cs, bs_log2, xyz, idxs, new_xyz, identity_flag, stream);
 }
 
 constexpr int kPtsOptions[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
@@ -809,7 +667,7 @@ PN2_EXPORT int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz
     const char *e = getenv("PN2_FPS_PREFIX");
     return e == nullptr || e[0] != '0';
   }();
-  if (prefix_on && fps_multipick_enabled() && pts != 0 && temp != nullptr && n <= kPrefixMaxN && m >= 2 && m < n &&
+  if (prefix_on && pts != 0 && temp != nullptr && n <= kPrefixMaxN && m >= 2 && m < n &&
       b <= 65535) {
     float *diag = temp;
     int *flag = reinterpret_cast<int *>(temp + static_cast<size_t>(b) * m);

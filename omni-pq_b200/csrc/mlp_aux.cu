@@ -393,9 +393,9 @@ static int transpose_launch(bool to_pm, int b, int c, int n, int ld, int stride,
   dim3 grid((n + 31) / 32, (cc + 31) / 32, b);
   PN2_REQUIRE(grid.y <= 65535, "%s: too many channels", what);
   if (to_pm)
-    pn2::launch_small(to_point_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, ld, stride, src, dst);
+    pn2::launch(to_point_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, ld, stride, src, dst);
   else
-    pn2::launch_small(to_channel_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, stride, src, dst);
+    pn2::launch(to_channel_major_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), c, n, stride, src, dst);
   return check_launch(what);
 }
 
@@ -409,7 +409,7 @@ PN2_EXPORT int pn2_to_channel_major(int b, int c, int n, int stride, const float
 PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, double count, const float *stats, double *sums,
                                    void *stream) {
   PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
-  pn2::launch_small(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, count, stats, sums);
+  pn2::launch(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, count, stats, sums);
   return check_launch("pn2_bn_reduce_stats");
 }
 
@@ -421,12 +421,12 @@ PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double co
   PN2_REQUIRE(training ? ((stats && count > 0.0) || sums) : (running_mean && running_var),
               "pn2_bn_finalize: %s", training ? "training needs statistics and a positive count" : "eval needs running statistics");
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  pn2::launch_small(bn_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, s, training, tiles, c, np, count, stats, sums, gamma, beta,
+  pn2::launch(bn_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, s, training, tiles, c, np, count, stats, sums, gamma, beta,
                                                        running_mean, running_var, num_batches_tracked, momentum, eps,
                                                        scale, shift, mean, invstd);
   if (int rc = check_launch("pn2_bn_finalize")) return rc;
   if (training && num_batches_tracked && running_mean && momentum < 0.f) {
-    pn2::launch_small(bn_bump_counter_kernel, dim3(1), dim3(1), 0, s, num_batches_tracked);
+    pn2::launch(bn_bump_counter_kernel, dim3(1), dim3(1), 0, s, num_batches_tracked);
     return check_launch("pn2_bn_finalize(counter)");
   }
   return PN2_OK;
@@ -439,7 +439,7 @@ PN2_EXPORT int pn2_bn_relu_pool(int groups, int group, int c, int ld, const floa
   if (groups == 0) return PN2_OK;
   PN2_REQUIRE(y && scale && shift && out_pm, "pn2_bn_relu_pool: null pointer");
   const long long total = static_cast<long long>(groups) * (ld / 4);
-  pn2::launch_small(bn_relu_pool_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+  pn2::launch(bn_relu_pool_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       groups, group, ld, y, scale, shift, out_pm, arg);
   return check_launch("pn2_bn_relu_pool");
 }
@@ -452,7 +452,7 @@ PN2_EXPORT int pn2_pool_bwd_prep(int groups, int group, int c, int ld, float *gz
   if (tiles) *tiles = pn2_pool_bwd_tiles(groups);
   if (groups == 0) return PN2_OK;
   PN2_REQUIRE(gz && out_pm && y && stats && (arg || group == 1), "pn2_pool_bwd_prep: null pointer");
-  pn2::launch_small(pool_bwd_prep_kernel, dim3(pn2_pool_bwd_tiles(groups)), dim3(128), 0, static_cast<cudaStream_t>(stream), groups, group, ld, gz,
+  pn2::launch(pool_bwd_prep_kernel, dim3(pn2_pool_bwd_tiles(groups)), dim3(128), 0, static_cast<cudaStream_t>(stream), groups, group, ld, gz,
                                                                                                 out_pm, arg, y, stats);
   return check_launch("pn2_pool_bwd_prep");
 }
@@ -463,7 +463,7 @@ PN2_EXPORT int pn2_bn_bwd_finalize(int training, int tiles, int c, int np, doubl
                                    void *stream) {
   PN2_REQUIRE(c > 0 && np >= c && (stats || sums) && mean && invstd && ca && cb && cc && (count > 0.0 || count_dev),
               "pn2_bn_bwd_finalize: bad arguments");
-  pn2::launch_small(bn_bwd_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), 
+  pn2::launch(bn_bwd_finalize_kernel, dim3((np + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), 
       training, tiles, c, np, count, stats, sums, count_dev, gamma, mean, invstd, ca, cb, cc, dgamma, dbeta);
   return check_launch("pn2_bn_bwd_finalize");
 }

@@ -406,7 +406,7 @@ PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_p
   long long total = static_cast<long long>(kp) * np;
   if (img_t > total) total = img_t;
   if (img_p > total) total = img_p;
-  pn2::launch_small(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+  pn2::launch(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p);
   return check_launch("pn2_mlp_prep_weights");
 }
@@ -565,10 +565,10 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   if (wide && nsl >= 64) {  // few, large slices (big outputs): the thread-per-element kernel is faster (measured)
     int nw = 1;
     while (nw < 16 && nw < nsl) nw *= 2;
-    pn2::launch_small(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,
+    pn2::launch(wgrad_reduce_wide_kernel, dim3((total + 31) / 32), dim3(32 * nw), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl,
                 ws, dw);
   } else {
-    pn2::launch_small(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl, ws, dw);
+    pn2::launch(wgrad_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, cout, cin, xyz_first, feat_pad, kp, np, nsl, ws, dw);
   }
   return check_launch("pn2_mlp_wgrad(reduce)");
 }

@@ -1,23 +1,22 @@
-// Shared-MLP contraction on the 5th-generation tensor cores (tcgen05, sm_100a): same operands, row sources
-// and epilogues as the FFMA kernel in mlp_gemm.cu, for the forward and data-gradient GEMMs
-// (C[M x N] = A[M x K] * B[N x K]^T with both operands K-major).
+// Shared-MLP contraction on the 5th-generation tensor cores (tcgen05, sm_100a): same operands, row sources and
+// epilogues as the FFMA kernel in mlp_gemm.cu (C[M x N] = A[M x K] * B[N x K]^T).
 //
-// Precision: the parity bar of the float paths is 1e-5 relative, which a single TF32 pass (10-bit mantissa)
-// cannot meet.  Every fp32 operand is split while it is staged into  v = hi + lo  (hi = nearest tf32,
-// lo = v - hi exactly) and each k-step issues three kind::tf32 MMAs, hi*hi + hi*lo + lo*hi, accumulated in
-// fp32 in tensor memory; the dropped lo*lo term is below 2^-22 relative per product.
+// Precision: the parity bar of the float paths is 1e-5 relative, which a single TF32 pass (10-bit mantissa) cannot
+// meet.  Every fp32 operand is split while it is staged into  v = hi + lo  (hi = nearest tf32 of v, lo = nearest tf32
+// of v - hi) and each 8-wide k-step issues three kind::tf32 MMAs, hi*hi + hi*lo + lo*hi, accumulated in fp32 in tensor
+// memory; the dropped lo*lo term is below 2^-22 relative per product.  Measured against float64 the result is
+// 1e-6 ... 7e-6 relative over the backbone's layer stacks (fp32 FMA: 3e-7): the tensor core adds into its fp32
+// accumulator with truncation, 3 x K/8 times per output (tests/arbiter.py has the numbers).
 //
-// Structure (one CTA = one 128 x 128 output tile, 256 threads, 1 CTA/SM):
-//   * all 8 warps are producers: they evaluate the row source (gather / BN+ReLU / BN-backward ...) for a
-//     128 x 32 k-block of A and of B, split it and store hi/lo tiles in the canonical K-major 128-byte-swizzle
-//     layout the UMMA descriptor expects (conflict-free 128-bit stores), 3-stage ring;
-//   * fence.proxy.async + one barrier per k-block, then ONE thread issues 12 tcgen05.mma (4 k-steps x 3 split
-//     terms) and commits them to the stage's "empty" mbarrier, so the tensor pipe works on block i while the
-//     producers stage block i+1, i+2;
-//   * epilogue: accumulator tile read back with tcgen05.ld (each thread one row, 32 columns at a time),
-//     stored with 128-byte row segments; BatchNorm partial column sums by a warp butterfly transpose-reduce.
-// The operands are produced by threads rather than TMA because every A element needs an element-wise
-// transform (that fusion is the point of the kernel); the weights are small and L2 resident.
+// Two kernels:
+//   * gemm_tc_async_kernel  -- forward and data-gradient GEMMs (A = a row source with its element-wise transform,
+//     B = the layer's weights): persistent, one CTA per SM, 16 producer warps + a converged MMA warp + a weight-loader
+//     warp; activations travel  global --cp.async--> raw ring in shared memory --transform, split--> TENSOR MEMORY
+//     (tcgen05.st), weights as a pre-split image by cp.async.bulk; MMAs in TS form (A from tensor memory).
+//   * gemm_tc_kernel<.., TRANS = true, ..>  -- weight-gradient GEMMs (K = positions): both operands are row sources,
+//     staged MN-major through registers by 16 producer warps, one CTA per (tile, position slice).
+// Both share the epilogue (tcgen05.ld -> per-warp shared-memory transpose -> row-contiguous 128-bit stores, BatchNorm
+// partial column sums, ReLU-mask / scatter-add variants).
 #include <atomic>
 
 #include "mlp_rows.cuh"
@@ -449,9 +448,8 @@ gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
     // per warp and reclaimed when the MMAs that read it have completed
     // ROT = false: the two prefetch register sets are addressed with compile-time indices (loop unrolled by 2);
-    // ROT = true: one loop body, the sets are rotated with register copies (fewer live registers, but the copy
-    // waits for the load it has just issued).  PN2_TC_ROT selects; both are kept until one is measured better
-    // on every shape.
+    // ROT = true (what launch_tc instantiates): one loop body, the sets are rotated with register copies (fewer live
+    // registers; the copy waits for the load it has just issued).
     constexpr int NU = ROT ? 1 : 2;
     for (int kb0 = 0; kb0 < num_kb; kb0 += NU) {
 #pragma unroll
@@ -992,14 +990,9 @@ int launch_tc_rot(const GemmArgs &g, int splits, cudaStream_t stream) {
 
 template <int AKIND, int BKIND, bool TRANS, int EPI>
 int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
-  // measured (profiles/c8_*): the same per-k-block time on plain shapes, but the statically indexed sets spill
-  // under the 96-register cap of a 17-warp CTA for the DYPOOL / GATHER sources (wgrad 1.31 vs 1.09 ms per step)
-  static const bool rot = [] {
-    const char *e = getenv("PN2_TC_ROT");
-    return e == nullptr || e[0] != '0';
-  }();
-  return rot ? launch_tc_rot<AKIND, BKIND, TRANS, EPI, true>(g, splits, stream)
-             : launch_tc_rot<AKIND, BKIND, TRANS, EPI, false>(g, splits, stream);
+  // prefetch register sets rotated with copies (ROT = true): the statically indexed variant spills under the 96-register
+  // cap of a 17-warp CTA for the DYPOOL / GATHER sources (wgrad 1.31 vs 1.09 ms per step, profiles/r1_c8_*)
+  return launch_tc_rot<AKIND, BKIND, TRANS, EPI, true>(g, splits, stream);
 }
 
 }  // namespace
@@ -1027,15 +1020,9 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
   if (akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER && g.K > 640) return PN2_TC_UNSUPPORTED;  // coefficient staging
-  // PN2_TC_BULK=0 keeps every operand thread-staged (gemm_tc_kernel) for A/B measurements
-  static const bool bulk_on = [] {
-    const char *e = getenv("PN2_TC_BULK");
-    return e == nullptr || e[0] != '0';
-  }();
-  const bool use_bulk = bulk_on && g.b_img != nullptr;
-#define PN2_TC_CASE(AK, EP)                                                                     \
-  if (akind == AK && epi == EP)                                                                 \
-    return !use_bulk ? launch_tc<AK, PN2_ROWS_PLAIN, false, EP>(g, 1, stream) : launch_tc_async<AK, EP>(g, stream);
+  if (g.b_img == nullptr) return PN2_TC_UNSUPPORTED;  // the weight operand comes as the pre-split image only
+#define PN2_TC_CASE(AK, EP) \
+  if (akind == AK && epi == EP) return launch_tc_async<AK, EP>(g, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_BNRELU, TC_EPI_STORE_STATS)
   PN2_TC_CASE(PN2_ROWS_GATHER, TC_EPI_STORE_STATS)

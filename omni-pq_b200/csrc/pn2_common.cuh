@@ -46,40 +46,15 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 // whatever SM resources are free) and then waits until the PREVIOUS kernel has completed and its writes are
 // visible (griddepcontrol.wait) before touching memory.  Launches go through pn2::launch(), which sets the
 // programmatic-stream-serialization attribute when PN2_PDL=1 (the device instructions are no-ops otherwise).
-// Measured on the backbone step it is SLOWER (4.21 vs 3.94 ms): the early-scheduled CTAs of the next kernel hold SM
-// resources the geometry stream's kernels and the running kernel's later waves need.  Off by default.
+// Measured on the backbone step it is SLOWER (4.21 vs 3.94 ms in round 1; restricted to the small finalize / reduce /
+// layout kernels in round 2: 3.64 vs 3.56 ms): the early-scheduled CTAs of the next kernel hold SM resources the
+// geometry stream's kernels and the running kernel's later waves need.  Off by default.
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool pdl_enabled();
-bool pdl_small_enabled();  // PN2_PDL_SMALL: the attribute on the SMALL kernels only (finalize / reduce / layout / prep)
 void note_launch();  // counts every kernel launch of the library (pn2_kernel_launches())
-
-template <typename... P, typename... A>
-inline cudaError_t launch_attr(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                               A &&...args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  note_launch();
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
-}
-
-// Small kernels between two GEMMs (BatchNorm finalize, split reductions, layout changes, weight preparation): a few
-// CTAs that run for 2-5 us, i.e. about as long as their own launch latency.  With the programmatic attribute their
-// launch overlaps the tail of the kernel in front of them (they still wait for its completion in pdl_prologue()).
-template <typename... P, typename... A>
-inline cudaError_t launch_small(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args) {
-  return launch_attr(pdl_enabled() || pdl_small_enabled(), kernel, grid, block, smem, stream, static_cast<A &&>(args)...);
-}
 
 template <typename... P, typename... A>
 inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args) {

@@ -52,14 +52,6 @@ bool pdl_enabled() {
   return on;
 }
 
-bool pdl_small_enabled() {
-  static const bool on = [] {
-    const char *e = getenv("PN2_PDL_SMALL");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 }  // namespace pn2
 
 PN2_EXPORT int pn2_version(void) { return 100; }
