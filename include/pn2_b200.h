@@ -164,6 +164,16 @@ int pn2_mlp_tiles(int rows, int np); /* row tiles pn2_mlp_forward / pn2_mlp_dgra
  * DEVICE (no host synchronisation).  training == 0: running statistics.  gamma/beta may be NULL (affine=False).
  * momentum < 0 means cumulative average. */
 int pn2_bn_reduce_stats(int tiles, int c, int np, double count, const float *stats, double *sums, void *stream);
+/* SyncBatchNorm exchange fused into the statistics kernel (replaces pn2_bn_reduce_stats + the caller's all-reduce):
+ * `peers[r]` = device address, in THIS process, of rank r's exchange buffer (symmetric / peer-mapped memory;
+ * 2 * slot_doubles doubles + `world` 32-bit signal words, zero-filled once, slot_doubles >= 2c+2); `epoch` = 1, 2, 3 ...
+ * incremented by the caller for every exchange (identically on every rank); `cta_ticket` = a zeroed device word.
+ * Writes sums[2c+1] = totals and row count over all ranks.  Every rank of the group must issue the same sequence of
+ * exchanges; a peer that never arrives makes the kernel trap after ~2 s (CUDA error) rather than hang.  Not for use
+ * inside CUDA-graph capture (the epoch is a launch argument). */
+int pn2_bn_sync_exchange(int tiles, int c, int np, double count, const float *stats, const unsigned long long *peers,
+                         int rank, int world, unsigned epoch, int slot_doubles, unsigned *cta_ticket, double *sums,
+                         void *stream);
 int pn2_bn_finalize(int training, int tiles, int c, int np, double count, const float *stats, const double *sums,
                     const float *gamma, const float *beta, float *running_mean, float *running_var,
                     long long *num_batches_tracked, float momentum, float eps, float *scale, float *shift,

@@ -339,6 +339,7 @@ _prep = _sig("pn2_mlp_prep_weights", _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
 _mlp_fwd = _sig("pn2_mlp_forward", _rp, _i, _i, _vp, _vp, _vp, _i, _vp, _ip_, _vp)
 _mlp_tiles = _sig("pn2_mlp_tiles", _i, _i, kernel=False)
 _bn_reduce = _sig("pn2_bn_reduce_stats", _i, _i, _i, _d, _vp, _vp, _vp)
+_bn_sync = _sig("pn2_bn_sync_exchange", _i, _i, _i, _d, _vp, _vp, _i, _i, ctypes.c_uint, _i, _vp, _vp, _vp)
 _bn_fin = _sig("pn2_bn_finalize", _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp)
 _pool = _sig("pn2_bn_relu_pool", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
 _to_pm = _sig("pn2_to_point_major", _i, _i, _i, _i, _i, _vp, _vp, _vp)
@@ -395,6 +396,15 @@ def bn_reduce_stats(stats, tiles, c, np_, count):
     on the device, so the exchange needs no host synchronisation)."""
     sums = torch.empty(2 * c + 1, dtype=torch.float64, device=stats.device)
     _check(_bn_reduce(tiles, c, np_, float(count), _ptr(stats), _ptr(sums), _stream()))
+    _launched()
+    return sums
+
+
+def bn_sync_exchange(stats, tiles, c, np_, count, peers, rank, world, epoch, slot_doubles, ticket):
+    """Statistics reduction + cross-rank exchange over peer memory in one kernel -> sums [2c+1] over all ranks."""
+    sums = torch.empty(2 * c + 1, dtype=torch.float64, device=stats.device)
+    _check(_bn_sync(tiles, c, np_, float(count), _ptr(stats), _ptr(peers), rank, world, epoch, slot_doubles, _ptr(ticket),
+                    _ptr(sums), _stream()))
     _launched()
     return sums
 

@@ -116,6 +116,94 @@ bn_reduce_stats_kernel(int tiles, int c, int np, double count, const float *__re
   sums[c + ch] = s2;
 }
 
+// ---- SyncBatchNorm: statistics reduction + cross-rank exchange in ONE kernel, over NVLink peer memory -----------------
+// (models/pq_transformer.py:194 converts every hot-path BatchNorm into a SyncBatchNorm, which torch
+// serves with an all_gather + an all_reduce and their host-side bookkeeping per layer: 38 small NCCL collectives per
+// step on the path.)  Every rank owns a buffer in symmetric memory (torch.distributed._symmetric_memory: the same
+// allocation mapped into every peer's address space): [2 slots][2c+2 doubles] + one 32-bit signal word per sender.
+//   1. each CTA reduces its 8 channels' per-tile partials to fp64 totals (as bn_reduce_stats_kernel) and stores them
+//      into THIS rank's slot (epoch parity); CTA 0 adds the rank's row count;
+//   2. the last CTA to finish (device-scope ticket) publishes the slot: one st.release.sys of the epoch number into
+//      every peer's signal word for this rank -- the only "send" of the exchange;
+//   3. every CTA waits until all peers' signal words have reached the epoch (ld.acquire.sys; traps after ~2 s instead of
+//      hanging the GPU) and then LOADS the peers' totals of its 8 channels straight from their memory over NVLink,
+//      adding them in rank order -- every rank computes bit-identical totals, no reduction tree, no second kernel.
+// Output: sums[2c+1] = (sum, second sum, row count) over all ranks, consumed on the device by the finalize kernels.
+// Slot reuse is safe with two slots: a rank can enter exchange e+2 only after every peer has signalled e+1, i.e. after
+// the peers' kernels of exchange e (which read this rank's slot e) have completed.
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kStatCh * kStatLanes)
+bn_sync_exchange_kernel(int tiles, int c, int np, double count, const float *__restrict__ stats,
+                        const unsigned long long *__restrict__ peers /* [world] base address of every rank's buffer */,
+                        int rank, int world, unsigned epoch, int slot_doubles, unsigned *__restrict__ cta_ticket,
+                        double *__restrict__ sums) {
+  pdl_prologue();
+  const int ch = blockIdx.x * kStatCh + threadIdx.x % kStatCh;
+  const bool writer = threadIdx.x / kStatCh == 0 && ch < c;
+  double s1, s2;
+  total_of(stats, tiles, np, ch, ch < c, s1, s2);
+  double *mine = reinterpret_cast<double *>(peers[rank]) + static_cast<size_t>(epoch & 1u) * slot_doubles;
+  if (writer) {
+    mine[ch] = s1;
+    mine[c + ch] = s2;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) mine[2 * c] = count;
+  __threadfence_system();  // this thread's slot stores are visible system-wide before the ticket below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(cta_ticket, 1u);
+    if (done == gridDim.x - 1) {  // every CTA of this rank has stored and fenced its part of the slot: publish it
+      *cta_ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) {
+        unsigned *sig = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(peers[r]) + 2 * slot_doubles) + rank;
+        st_release_sys_u32(sig, epoch);
+      }
+    }
+    const unsigned *my_sig = reinterpret_cast<const unsigned *>(reinterpret_cast<double *>(peers[rank]) + 2 * slot_doubles);
+    long long t0 = 0;
+    for (int r = 0; r < world; ++r) {
+      unsigned spins = 0;
+      while (static_cast<int>(ld_acquire_sys_u32(my_sig + r) - epoch) < 0) {  // wrap-safe "signal < epoch"
+        if ((++spins & 1023u) == 0) {
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000ll) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!writer && !(blockIdx.x == 0 && threadIdx.x == 0)) return;
+  double t1 = 0.0, t2 = 0.0, n = 0.0;
+  for (int r = 0; r < world; ++r) {  // fixed rank order: bit-identical totals on every rank
+    const double *theirs = reinterpret_cast<const double *>(peers[r]) + static_cast<size_t>(epoch & 1u) * slot_doubles;
+    if (writer) {
+      t1 += ld_relaxed_sys_f64(theirs + ch);
+      t2 += ld_relaxed_sys_f64(theirs + c + ch);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) n += ld_relaxed_sys_f64(theirs + 2 * c);
+  }
+  if (writer) {
+    sums[ch] = t1;
+    sums[c + ch] = t2;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * c] = n;
+}
+
 __global__ void bn_finalize_kernel(int training, int tiles, int c, int np, double count,
                                    const float *__restrict__ stats, const double *__restrict__ sums,
                                    const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -411,6 +499,20 @@ PN2_EXPORT int pn2_bn_reduce_stats(int tiles, int c, int np, double count, const
   PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && sums, "pn2_bn_reduce_stats: bad arguments");
   pn2::launch(bn_reduce_stats_kernel, dim3((c + kStatCh - 1) / kStatCh), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np, count, stats, sums);
   return check_launch("pn2_bn_reduce_stats");
+}
+
+PN2_EXPORT int pn2_bn_sync_exchange(int tiles, int c, int np, double count, const float *stats,
+                                    const unsigned long long *peers, int rank, int world, unsigned epoch, int slot_doubles,
+                                    unsigned *cta_ticket, double *sums, void *stream) {
+  PN2_REQUIRE(tiles >= 0 && c > 0 && np >= c && stats && peers && cta_ticket && sums, "pn2_bn_sync_exchange: bad arguments");
+  PN2_REQUIRE(world >= 1 && rank >= 0 && rank < world && slot_doubles >= 2 * c + 2 && epoch != 0,
+              "pn2_bn_sync_exchange: bad exchange geometry (world=%d rank=%d slot=%d c=%d epoch=%u)", world, rank, slot_doubles,
+              c, epoch);
+  const int grid = (c + kStatCh - 1) / kStatCh;
+  PN2_REQUIRE(grid <= sm_count(), "pn2_bn_sync_exchange: %d CTAs must be co-resident (they wait for each other's peers)", grid);
+  pn2::launch(bn_sync_exchange_kernel, dim3(grid), dim3(kStatCh * kStatLanes), 0, static_cast<cudaStream_t>(stream), tiles, c, np,
+              count, stats, peers, rank, world, epoch, slot_doubles, cta_ticket, sums);
+  return check_launch("pn2_bn_sync_exchange");
 }
 
 PN2_EXPORT int pn2_bn_finalize(int training, int tiles, int c, int np, double count, const float *stats,

@@ -131,6 +131,60 @@ def all_reduce_stats(sums, group):
     return sums
 
 
+class _PeerExchange:
+    """Per process group: this rank's exchange buffer in symmetric memory (mapped into every peer) and what
+    pn2_bn_sync_exchange needs to find the peers'.  Built lazily by the first SyncBatchNorm layer that runs; if symmetric
+    memory cannot be set up (no peer access, older driver) `ok` stays False and the NCCL all-reduce is used."""
+    SLOT = 2 * 2048 + 2  # doubles per slot: up to 2048 channels
+
+    def __init__(self, group, device):
+        self.ok, self.why = False, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)  # needed by older torch, a deprecated no-op later
+            except Exception:
+                pass
+            n = 2 * self.SLOT + (self.world + 1) // 2 + 1
+            self.buf = symm.empty(n, dtype=torch.float64, device=device)
+            self.buf.zero_()
+            self.hdl = symm.rendezvous(self.buf, group)
+            self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+            self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+            self.epoch = 0
+            torch.cuda.synchronize(device)
+            dist.barrier(group)  # every rank's buffer is zeroed before anybody signals into it
+            self.ok = True
+        except Exception as ex:  # fall back to NCCL; the reason is kept for diagnostics
+            self.why = f"{type(ex).__name__}: {ex}"
+
+    def exchange(self, stats, tiles, c, np_, count):
+        self.epoch += 1
+        return K.bn_sync_exchange(stats, tiles, c, np_, count, self.peers, self.rank, self.world, self.epoch, self.SLOT,
+                                  self.ticket)
+
+
+_peer_exchanges = {}
+_PEER_EXCHANGE = os.environ.get("PN2_SYNCBN_PEER", "1") != "0"  # PN2_SYNCBN_PEER=0: always exchange with NCCL
+peer_exchange_calls = 0  # exchanges served by the fused kernel (tests read this)
+
+
+def exchange_stats(stats, tiles, c, np_, count, group):
+    """SyncBatchNorm totals over all ranks, [2c+1] fp64 on the device: the fused peer-memory kernel when symmetric memory
+    is available and no CUDA graph is being captured (its epoch is a launch argument), else reduce + NCCL all-reduce."""
+    global peer_exchange_calls
+    if _PEER_EXCHANGE and c <= 2048 and not torch.cuda.is_current_stream_capturing():
+        key = (id(group), stats.device.index)
+        ex = _peer_exchanges.get(key)
+        if ex is None:
+            ex = _peer_exchanges[key] = _PeerExchange(group, stats.device)
+        if ex.ok:
+            peer_exchange_calls += 1
+            return ex.exchange(stats, tiles, c, np_, count)
+    return all_reduce_stats(K.bn_reduce_stats(stats, tiles, c, np_, count), group)
+
+
 class _Layer:
     """Per-layer forward state kept for the backward pass."""
     __slots__ = ("cout", "cin", "kp", "np", "xyz_first", "feat_pad", "wt", "wp", "y", "scale", "shift", "mean",
@@ -145,7 +199,7 @@ def _bn_forward(L, bn, stats, tiles, rows):
     if training:
         pg = _sync_group(bn)
         if pg is not None:
-            sums = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np, rows), pg)
+            sums = exchange_stats(stats, tiles, L.cout, L.np, rows, pg)
             L.group, L.count_dev = pg, sums[2 * L.cout:]  # global row count, device resident
         elif rows <= 1:
             raise ValueError("Expected more than 1 value per channel when training")
@@ -186,7 +240,7 @@ def _bn_backward(L, stats, tiles):
     like torch.nn.SyncBatchNorm's backward."""
     sums = None
     if L.group is not None:
-        sums = all_reduce_stats(K.bn_reduce_stats(stats, tiles, L.cout, L.np, 0), L.group)
+        sums = exchange_stats(stats, tiles, L.cout, L.np, 0, L.group)
     return K.bn_bwd_finalize(L.training, tiles, L.cout, L.np, L.count, stats, sums, L.gamma.detach(), L.mean, L.invstd,
                              count_dev=L.count_dev, dgamma_out=_slot(L.params[1]), dbeta_out=_slot(L.params[2]))
 

@@ -89,7 +89,10 @@ def main():
             assert torch.equal(b1, b2), n1
     errs["buffers"] = bw
     ok = errs["sa_out"] <= 1e-5 and errs["fp_out"] <= 1e-5 and errs["d_feats"] <= 1e-4 and worst <= 1e-4 and bw <= 1e-5
-    print(f"rank {rank}: {'SYNCBN_OK' if ok else 'SYNCBN_FAIL'} {errs} worst_param={worst_name}", flush=True)
+    import fused
+    why = [ex.why for ex in fused._peer_exchanges.values() if not ex.ok]
+    print(f"rank {rank}: {'SYNCBN_OK' if ok else 'SYNCBN_FAIL'} {errs} worst_param={worst_name} "
+          f"peer_exchanges={fused.peer_exchange_calls} {why}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -36,3 +36,6 @@ def test_fused_syncbn_over_nccl_matches_torch_syncbn(built_lib):
         pytest.skip("oracle/_ref/pn2_ref_ext.so (reference kernels) not built")
     r = _torchrun("syncbn_worker.py", {"PN2_SYNCBN_BACKEND": "nccl"})
     assert r.returncode == 0 and r.stdout.count("SYNCBN_OK") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    print(r.stdout[-600:])
+    # over NVLink peers the exchange must have been served by the fused kernel (4 BatchNorm layers x 2 directions)
+    assert r.stdout.count("peer_exchanges=8 []") == 2, r.stdout[-1500:]
