@@ -268,32 +268,32 @@ __device__ __forceinline__ int orig_cin(int kq, int cin, int xyz_first, int feat
   return d < 3 ? d : -1;
 }
 
-// Tensor-core image of a K-major operand matrix B [rows][cols] (mlp_gemm_tc.cu, gemm_tc_bulk_kernel): for every
-// (128-row tile, 32-column k-block) one 32 KB stage = [hi 16 KB | lo 16 KB], each half in the UMMA K-major
-// 128-byte-swizzle layout (row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c XOR (r%8)), zero padded.
-constexpr int IMG_STAGE_FLOATS = 2 * 128 * 32;
-__host__ __device__ inline long long img_floats(int rows, int cols) {
-  return static_cast<long long>((rows + 127) / 128) * ((cols + 31) / 32) * IMG_STAGE_FLOATS;
+// Tensor-core image of a K-major operand matrix B [rows][cols] (mlp_gemm_tc.cu, gemm_tc_async_kernel): for every
+// (R-row tile, 32-column k-block) one stage = [hi R x 32 | lo R x 32] floats, each half in the UMMA K-major
+// 128-byte-swizzle layout (row r at (r/8)*1024 + (r%8)*128 bytes, 16-byte chunk c XOR (r%8)), zero padded.
+// R = 256 when the matrix has a multiple of 256 rows (the kernel then runs 128 x 256 tiles), else 128.
+inline int img_tile_rows(int rows) { return (gemm_tc_wide_enabled() && rows % 256 == 0) ? 256 : 128; }
+inline long long img_floats(int rows, int cols) {  // (the same for either tile height)
+  return static_cast<long long>((rows + 127) / 128) * ((cols + 31) / 32) * (2 * 128 * 32);
 }
-__device__ __forceinline__ void img_store(float *img, int cols, long long e, float v) {
-  // e enumerates (tile, k-block, row-in-tile, col-in-block); returns through img the hi / lo placement
-  const int c = static_cast<int>(e & 31), r = static_cast<int>((e >> 5) & 127);
-  const long long stage = e >> 12;
+// e enumerates (tile, k-block, row-in-tile, col-in-block) of a matrix imaged with R-row tiles
+__device__ __forceinline__ void img_store(float *img, int R, long long e, float v) {
+  const int c = static_cast<int>(e & 31), r = static_cast<int>((e >> 5) % R);
+  const long long stage = e / (32 * R);
   uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
   const float hi = __uint_as_float(h);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));  // rounded, not left to the tensor core's truncation
   const float lo = __uint_as_float(l);
-  const int off = (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));  // floats inside a 16 KB half
-  float *st = img + stage * IMG_STAGE_FLOATS;
+  const int off = (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));  // floats inside a half
+  float *st = img + stage * (2 * R * 32);
   st[off] = hi;
-  st[4096 + off] = lo;
-  (void)cols;
+  st[R * 32 + off] = lo;
 }
 
 __global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp, int np,
                                     const float *__restrict__ w, float *__restrict__ wt, float *__restrict__ wp,
-                                    long long img_t, long long img_p) {
+                                    long long img_t, long long img_p, int rows_t, int rows_p) {
   pdl_prologue();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < static_cast<long long>(kp) * np) {
@@ -309,20 +309,20 @@ __global__ void prep_weights_kernel(int cout, int cin, int xyz_first, int feat_p
     }
   }
   if (i < img_t) {  // image of wt: operand rows = k (kp of them), operand columns = n
-    const int nkb = (np + 31) / 32;
-    const long long stage = i >> 12;
-    const int k = static_cast<int>(stage / nkb) * 128 + static_cast<int>((i >> 5) & 127);
+    const int R = rows_t, nkb = (np + 31) / 32;
+    const long long stage = i / (32 * R);
+    const int k = static_cast<int>(stage / nkb) * R + static_cast<int>((i >> 5) % R);
     const int n = static_cast<int>(stage % nkb) * 32 + static_cast<int>(i & 31);
     const int c = k < kp ? orig_cin(k, cin, xyz_first, feat_pad) : -1;
-    img_store(wt + static_cast<size_t>(kp) * np, np, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
+    img_store(wt + static_cast<size_t>(kp) * np, R, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
   }
   if (i < img_p) {  // image of wp: operand rows = n, operand columns = k
-    const int nkb = (kp + 31) / 32;
-    const long long stage = i >> 12;
-    const int n = static_cast<int>(stage / nkb) * 128 + static_cast<int>((i >> 5) & 127);
+    const int R = rows_p, nkb = (kp + 31) / 32;
+    const long long stage = i / (32 * R);
+    const int n = static_cast<int>(stage / nkb) * R + static_cast<int>((i >> 5) % R);
     const int k = static_cast<int>(stage % nkb) * 32 + static_cast<int>(i & 31);
     const int c = k < kp ? orig_cin(k, cin, xyz_first, feat_pad) : -1;
-    img_store(wp + static_cast<size_t>(kp) * np, kp, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
+    img_store(wp + static_cast<size_t>(kp) * np, R, i, (n < cout && c >= 0) ? w[static_cast<size_t>(n) * cin + c] : 0.f);
   }
 }
 
@@ -407,7 +407,7 @@ PN2_EXPORT int pn2_mlp_prep_weights(int cout, int cin, int xyz_first, int feat_p
   if (img_t > total) total = img_t;
   if (img_p > total) total = img_p;
   pn2::launch(prep_weights_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p);
+      cout, cin, xyz_first, feat_pad, kp, np, w, wt, wp, img_t, img_p, img_tile_rows(kp), img_tile_rows(np));
   return check_launch("pn2_mlp_prep_weights");
 }
 
@@ -438,6 +438,7 @@ PN2_EXPORT int pn2_mlp_forward(const pn2_rows *a, int kp, int np, const float *w
     t.B = plain_rows(wp, np, kp, kp);
     t.b_img = wp + static_cast<size_t>(np) * kp;
     t.b_img_kblocks = (kp + 31) / 32;
+    t.b_tile_rows = img_tile_rows(np);
     const int rc = gemm_tc_launch(a->kind, EPI_STORE_STATS, &t, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }
@@ -477,6 +478,7 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
       t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
       t.b_img = wt + static_cast<size_t>(ncols) * dy->cols;
       t.b_img_kblocks = (dy->cols + 31) / 32;
+      t.b_tile_rows = img_tile_rows(ncols);
       const int rc = gemm_tc_launch(dy->kind, EPI_DGRAD_MASK, &t, s);
       if (rc != PN2_TC_UNSUPPORTED) return rc;
     }
@@ -490,6 +492,7 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
       t.B = plain_rows(wt, ncols, dy->cols, dy->cols);
       t.b_img = wt + static_cast<size_t>(ncols) * dy->cols;
       t.b_img_kblocks = (dy->cols + 31) / 32;
+      t.b_tile_rows = img_tile_rows(ncols);
       const int rc = gemm_tc_launch(dy->kind, EPI_STORE, &t, s);
       if (rc != PN2_TC_UNSUPPORTED) return rc;
     }
@@ -513,6 +516,7 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
     t2.B = plain_rows(wt, g.N, dy->cols, dy->cols);
     t2.b_img = wt + static_cast<size_t>(ncols) * dy->cols;  // the image follows the full [ncols][dy.cols] matrix
     t2.b_img_kblocks = (dy->cols + 31) / 32;
+    t2.b_tile_rows = img_tile_rows(ncols);
     const int rc = gemm_tc_launch(dy->kind, EPI_SCATTER, &t2, s);
     if (rc != PN2_TC_UNSUPPORTED) return rc;
   }

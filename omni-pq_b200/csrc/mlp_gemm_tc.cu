@@ -575,24 +575,27 @@ int *tile_counter_slot(int dev) {
 //   * weights: the pre-split image, one 32 KB bulk copy per k-block, 3-4 stage ring (as before).
 // 16 producer warps + one MMA warp (lane 0 issues) + one weight-loader warp (lane 0 issues the bulk copies, so that
 // waiting for a free weight stage never stalls a producer), one CTA per SM, dynamic tile tickets.
-constexpr int AS_NA = 6;
 constexpr int AS_CTA_THREADS = TC_THREADS + 64;
-constexpr uint32_t AS_TMEM_COLS = 512, AS_A_COL0 = 128, AS_A_STAGE_COLS = 64;  // per A stage: 32 hi + 32 lo columns
+constexpr uint32_t AS_TMEM_COLS = 512, AS_A_STAGE_COLS = 64;  // accumulator first, then the A stages: 32 hi + 32 lo columns each
 constexpr int AS_ARG_BYTES = TM * TK;                                             // uint8 arg-max slots of a k-block
 
-template <int AKIND>
+// TNW = tile width: 128, or 256 for weight matrices with a multiple of 256 rows -- A is then staged once per 256 output
+// columns and a k-block's 12 MMAs run 1536 cycles, above the producers' ~1650-cycle chain instead of far below it.
+template <int AKIND, int TNW>
 struct AsCfg {
   static constexpr bool kDz = AKIND == PN2_ROWS_DY || AKIND == PN2_ROWS_DYPOOL;
   static constexpr bool kArg = AKIND == PN2_ROWS_DYPOOL;
   static constexpr bool kCoef = !(AKIND == PN2_ROWS_PLAIN || AKIND == PN2_ROWS_GATHER);
   static constexpr int kRawBytes = TILE_BYTES * (kDz ? 2 : 1) + (kArg ? AS_ARG_BYTES : 0);
-  static constexpr int kNR = kDz ? 3 : 5;                // raw stages
-  static constexpr int kNB = kDz ? 3 : 4;                // weight stages
+  static constexpr int kBStage = 2 * TNW * TK * 4;                              // weight stage: hi + lo, 32 / 64 KB
+  static constexpr int kNR = kDz ? (TNW == 256 ? 2 : 3) : 5;                    // raw stages
+  static constexpr int kNB = TNW == 256 ? 2 : (kDz ? 3 : 4);                    // weight stages
+  static constexpr int kNA = (static_cast<int>(AS_TMEM_COLS) - TNW) / static_cast<int>(AS_A_STAGE_COLS);  // A stages: 6 / 4
   static constexpr int kCoefK = kCoef ? 640 : 0;         // largest K with per-channel coefficient vectors (else FFMA kernel)
-  static constexpr int kRing = kNB * BK_B_BYTES + kNR * kRawBytes;
+  static constexpr int kRing = kNB * kBStage + kNR * kRawBytes;
   static constexpr int kSmem = kRing + 1024 /*align*/ + 512 /*barriers, tickets*/ + 3 * kCoefK * 4;
   static_assert(kSmem + 4096 /*static: statistics partials*/ <= 232448, "shared memory budget");
-  static_assert(kNB * BK_B_BYTES >= (TC_THREADS / 32) * 32 * 36 * 4, "epilogue scratch aliases the weight ring");
+  static_assert(kNB * kBStage >= (TC_THREADS / 32) * 32 * 36 * 4, "epilogue scratch aliases the weight ring");
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
@@ -651,15 +654,17 @@ __device__ __forceinline__ ConsCtx cons_ctx(const pn2_rows &s, int row, bool wan
   return c;
 }
 
-template <int AKIND, int EPI>
+template <int AKIND, int EPI, int TNW>
 __global__ void __launch_bounds__(AS_CTA_THREADS, 1)  // 96 registers: more (__maxnreg__ 104 / 112) does not launch with 18 warps
 gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
-  using Cfg = AsCfg<AKIND>;
-  constexpr int NR = Cfg::kNR, NB = Cfg::kNB, NA = AS_NA;
+  using Cfg = AsCfg<AKIND, TNW>;
+  constexpr int NR = Cfg::kNR, NB = Cfg::kNB, NA = Cfg::kNA;
+  constexpr int BST = Cfg::kBStage;
+  constexpr uint32_t AS_A_COL0 = TNW;
   pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char *ring_b = tiles, *ring_r = tiles + NB * BK_B_BYTES;
+  unsigned char *ring_b = tiles, *ring_r = tiles + NB * BST;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + Cfg::kRing);
   uint64_t *full_b = bars, *empty_b = full_b + NB;            // weight stage landed / its MMAs done
   uint64_t *raw_full = empty_b + NB, *raw_empty = raw_full + NR;  // raw stage landed (512 async arrivals) / read (16 warps)
@@ -669,11 +674,11 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   int *ticket = reinterpret_cast<int *>(tmem_slot + 1);       // [8] ticket[ti & 7] = tile of this CTA's ti-th iteration
   float *coef_a = reinterpret_cast<float *>(tiles + Cfg::kRing + 512);  // [3][kCoefK]
   __shared__ float red[2][TC_THREADS / 32][32];
-  static_assert((2 * 4 + 2 * 6 + 2 * AS_NA + 2) * 8 + 4 + 32 <= 512, "barrier block");
+  static_assert((2 * NB + 2 * NR + 2 * NA + 2) * 8 + 4 + 32 <= 512, "barrier block");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp < TC_THREADS / 32;
-  const int ntn = (g.N + TN - 1) / TN;
+  const int ntn = (g.N + TNW - 1) / TNW;
   const int ntiles = ((g.M + TM - 1) / TM) * ntn;
   const int num_kb = (g.K + TK - 1) / TK;
   // Tile tickets: the first five of every CTA are STATIC (blockIdx + i * grid -- drawn dynamically up front, the CTAs that
@@ -705,7 +710,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(TM, TN, false);
+  const uint32_t idesc = idesc_tf32(TM, TNW, false);
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
   if (!producer) {
@@ -726,8 +731,8 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
           tc_fence_after_sync();
           if (kb == 0 && lane == 0) tile_stamp(ti, 6);
           const uint32_t a_hi = tmem_u + AS_A_COL0 + sa * AS_A_STAGE_COLS, a_lo = a_hi + 32;
-          const uint32_t bbase = smem_addr(ring_b + sb * BK_B_BYTES);
-          const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + TILE_BYTES);
+          const uint32_t bbase = smem_addr(ring_b + sb * BST);
+          const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + BST / 2);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < TK / 8; ++ks) {
@@ -750,13 +755,13 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
         const int tile = ticket[ti & 7];
         if (tile >= ntiles) break;
         const int n_tile = tile % ntn;
-        const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BK_B_BYTES / 4);
+        const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BST / 4);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % NB;
           if (it >= NB) mbar_wait_guarded(&empty_b[s], ((it / NB) - 1) & 1);  // the MMAs that read this stage are done
           if (kb == 0) tile_stamp(ti, 7);
-          mbar_expect_tx(&full_b[s], BK_B_BYTES);
-          bulk_g2s(ring_b + s * BK_B_BYTES, b_src + static_cast<size_t>(kb) * (BK_B_BYTES / 4), BK_B_BYTES, &full_b[s]);
+          mbar_expect_tx(&full_b[s], BST);
+          bulk_g2s(ring_b + s * BST, b_src + static_cast<size_t>(kb) * (BST / 4), BST, &full_b[s]);
         }
       }
     }
@@ -840,7 +845,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
         tile_stamp(ti, 0);
       }
       const int m_tile = tile / ntn, n_tile = tile - m_tile * ntn;
-      const int m0 = m_tile * TM, n0 = n_tile * TN;
+      const int m0 = m_tile * TM, n0 = n_tile * TNW;
       // contexts of the NEXT tile, resolved one tile ahead so that their (dependent) loads are long back when needed
       have_next = next_tile < ntiles;
       if (have_next) {
@@ -931,7 +936,12 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
       mbar_wait_guarded(done_bar, ti & 1);
       tc_fence_after_sync();
       if (tid == 0) tile_stamp(ti, 3);
-      tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, m_tile, 0, true, yv);  // scratch = the (idle) weight ring
+#pragma unroll
+      for (int h = 0; h < TNW / TN; ++h) {  // a 256-wide tile is drained as two 128-column halves
+        if (h > 0) tc_epilogue_prefetch<EPI>(g, m0, n0 + h * TN, yv);
+        tc_epilogue<EPI>(g, tmem_d + h * TN, tiles, red, m0, n0 + h * TN, m_tile, 0, true, yv);  // scratch = the (idle) weight ring
+        if (h + 1 < TNW / TN) producers_sync();  // the statistics partials of this half have been read
+      }
       tc_fence_before_sync();   // this warp's TMEM reads are complete before the next tile's first MMA can be issued
       producers_sync();
       if (tid == 0) tile_stamp(ti, 4);
@@ -949,10 +959,10 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, blockIdx.x, 5, static_cast<unsigned long long>(num_kb));
 }
 
-template <int AKIND, int EPI>
-int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
-  using Cfg = AsCfg<AKIND>;
-  auto kernel = gemm_tc_async_kernel<AKIND, EPI>;
+template <int AKIND, int EPI, int TNW>
+int launch_tc_async_w(const GemmArgs &g, cudaStream_t stream) {
+  using Cfg = AsCfg<AKIND, TNW>;
+  auto kernel = gemm_tc_async_kernel<AKIND, EPI, TNW>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -960,7 +970,7 @@ int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     configured_dev = dev;
   }
-  const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TN - 1) / TN);
+  const int ntiles = ((g.M + TM - 1) / TM) * ((g.N + TNW - 1) / TNW);
   const int sms = sm_count() - persistent_spare() > 1 ? sm_count() - persistent_spare() : 1;
   const int grid = ntiles < sms ? ntiles : sms;
   GemmArgs a = g;
@@ -969,6 +979,14 @@ int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
   if (a.tile_counter == nullptr) return check_launch("gemm_tc_async_kernel(counters)");
   pn2::launch(kernel, dim3(grid), dim3(AS_CTA_THREADS), Cfg::kSmem, stream, a);
   return check_launch("gemm_tc_async_kernel");
+}
+
+// 128 x 256 tiles when the weight image was built with 256-row tiles and the output width is a multiple of 256
+template <int AKIND, int EPI>
+int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
+  if (g.b_tile_rows == 256 && (g.N % 256) == 0) return launch_tc_async_w<AKIND, EPI, 256>(g, stream);
+  if (g.b_tile_rows != 128) return PN2_TC_UNSUPPORTED;
+  return launch_tc_async_w<AKIND, EPI, 128>(g, stream);
 }
 
 template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
@@ -1003,6 +1021,14 @@ static int g_trace_cap = 0;
 void gemm_trace_target(unsigned long long **buf, int *cap) {
   *buf = g_trace_buf;
   *cap = g_trace_cap;
+}
+
+bool gemm_tc_wide_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("PN2_TC_WIDE");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 bool gemm_tc_enabled() {

@@ -102,6 +102,7 @@ struct GemmArgs {
   // tcgen05 forward / dgrad: pre-split, pre-swizzled image of B (pn2_mlp_prep_weights), or null
   const float *b_img;
   int b_img_kblocks;
+  int b_tile_rows;    // rows per image tile: 256 when the weight matrix has a multiple of 256 rows, else 128
   // development aid (pn2_debug_gemm_trace): per-CTA phase timestamps [smid, start, prologue, main loop, end, k-blocks]
   unsigned long long *trace;
   int trace_cap;
@@ -115,6 +116,7 @@ constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
+bool gemm_tc_wide_enabled();  // PN2_TC_WIDE=0: 128 x 128 tiles (and weight images) everywhere
 void gemm_trace_target(unsigned long long **buf, int *cap);
 
 }  // namespace pn2
