@@ -365,9 +365,10 @@ wgrad_reduce_wide_kernel(int cout, int cin, int xyz_first, int feat_pad, int kp,
   dw[static_cast<size_t>(n) * cin + c] = t;
 }
 
-int wgrad_splits(int rows, int np, int kp) {
+// fold: the 4-column xyz block of a gathered source rides in the last feature tile (wgrad_fold_ok) -- one n-tile fewer
+int wgrad_splits(int rows, int np, int kp, bool fold = false) {
   if (gemm_tc_enabled()) {  // tcgen05 kernel: 128x128 tiles, 1 CTA/SM, position slices of >= 4 k-blocks of 32
-    const long long t = ((np + 127) / 128) * ((kp + 127) / 128);
+    const long long t = ((np + 127) / 128) * ((kp + 127) / 128 - (fold ? 1 : 0));
     // tiles * splits <= SMs: one wave (rounding up gave e.g. 6 x 25 = 150 CTAs on 148 SMs, i.e. a 2-CTA second wave).
     // Leaving 16 SMs to the geometry stream here as the persistent GEMMs do made no difference (3.079 vs 3.076 ms per step).
     long long s = static_cast<long long>(sm_count()) / t;
@@ -525,7 +526,8 @@ PN2_EXPORT int pn2_mlp_dgrad(int mode, const pn2_rows *dy, int ncols, const floa
 }
 
 PN2_EXPORT long long pn2_mlp_wgrad_workspace(int rows, int np, int kp) {
-  return static_cast<long long>(wgrad_splits(rows, np, kp)) * np * kp;
+  const int a = wgrad_splits(rows, np, kp), b = kp > 128 && kp % 128 == 4 ? wgrad_splits(rows, np, kp, true) : 0;
+  return static_cast<long long>(a > b ? a : b) * np * kp;
 }
 
 PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, int cin, int xyz_first, int feat_pad,
@@ -538,10 +540,11 @@ PN2_EXPORT int pn2_mlp_wgrad(const pn2_rows *dy, const pn2_rows *a, int cout, in
   PN2_REQUIRE(dy->rows == a->rows && ws && dw && cout <= dy->cols && cin <= a->cols, "pn2_mlp_wgrad: shapes disagree");
   const int np = dy->cols, kp = a->cols, rows = dy->rows;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  int splits = wgrad_splits(rows, np, kp);
   GemmArgs g = {};
   g.A = *dy; g.B = *a;
   g.M = np; g.N = kp; g.K = rows;
+  g.wg_fold = wgrad_fold_ok(&g) ? 1 : 0;
+  int splits = wgrad_splits(rows, np, kp, g.wg_fold != 0);
   g.k_per_split = ((rows + splits - 1) / splits + 31) / 32 * 32;  // multiple of both kernels' k-block
   g.out = ws; g.ldo = kp; g.out_split_stride = static_cast<long long>(np) * kp;
   int rc = PN2_TC_UNSUPPORTED;

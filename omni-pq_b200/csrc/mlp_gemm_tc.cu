@@ -135,38 +135,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
-// mbarrier wait that traps instead of hanging the GPU if a transaction count was ever wrong
+// mbarrier wait that traps instead of hanging the GPU if a transaction count was ever wrong.  The hot path -- the phase
+// is already complete -- is one try_wait and a branch: the producers' loops are instruction-issue bound, and the clock
+// bookkeeping of a guarded spin loop cost ~14 instructions per wait even when it never spun.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
   const uint32_t a = smem_addr(bar);
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (!done && (spins & 1023u) == 1023u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
-    }
-  }
-}
-
-// the same for the hot loops: two instructions when the phase is already complete (the guarded form above costs ~10),
-// a spin counter that traps after ~2^26 timed-out tries instead of the clock arithmetic
-__device__ __forceinline__ void mbar_wait_fast(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
-      "W%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra D%=;\n\t"
-      "add.u32 n, n, 1;\n\tsetp.gt.u32 p, n, 0x4000000;\n\t@p trap;\n\tbra W%=;\n\t"
-      "D%=:\n\t}" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
+  if (mbar_try_wait(a, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(a, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -609,24 +597,66 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ float4 lds4(const unsigned char *p) { return *reinterpret_cast<const float4 *>(p); }
+// shared-window loads with an explicit 32-bit address: base register + immediate, no generic-address arithmetic per load
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ int lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return static_cast<int>(v);
+}
+
+// apply_raw with the per-channel coefficient vectors read through the shared window (coef = 32-bit address of c0;
+// c1, c2 follow at coef_ld floats)
+template <int KIND>
+__device__ __forceinline__ float4 apply_raw_s(const pn2_rows &s, const RowCtx &c, int c4, const Raw &r, uint32_t coef, int coef_ld) {
+  if (!c.valid || c4 >= s.cols) return zero4();
+  if (KIND == PN2_ROWS_PLAIN) return r.x;
+  if (KIND == PN2_ROWS_GATHER) return c4 < s.feat_cols ? r.x : make_float4(c.gx, c.gy, c.gz, 0.f);
+  const float4 k0 = lds_v4(coef + c4 * 4), k1 = lds_v4(coef + (coef_ld + c4) * 4);
+  if (KIND == PN2_ROWS_BNRELU)
+    return make_float4(relu_nan(fmaf(r.x.x, k0.x, k1.x)), relu_nan(fmaf(r.x.y, k0.y, k1.y)),
+                       relu_nan(fmaf(r.x.z, k0.z, k1.z)), relu_nan(fmaf(r.x.w, k0.w, k1.w)));
+  const float4 k2 = lds_v4(coef + (2 * coef_ld + c4) * 4);
+  float4 dz = r.d;
+  if (KIND == PN2_ROWS_DYPOOL)
+    dz = make_float4(r.a.x == c.slot ? dz.x : 0.f, r.a.y == c.slot ? dz.y : 0.f, r.a.z == c.slot ? dz.z : 0.f,
+                     r.a.w == c.slot ? dz.w : 0.f);
+  return make_float4(fmaf(k2.x, r.x.x, fmaf(k0.x, dz.x, k1.x)), fmaf(k2.y, r.x.y, fmaf(k0.y, dz.y, k1.y)),
+                     fmaf(k2.z, r.x.z, fmaf(k0.z, dz.z, k1.z)), fmaf(k2.w, r.x.w, fmaf(k0.w, dz.w, k1.w)));
+}
 
 // what the ISSUING thread needs of a row: where it lives (element offsets, resolved once per tile)
 struct IssueCtx {
   bool valid;
-  size_t off, goff;
+  const float *px, *pd;  // the row in x; DY / DYPOOL: the row in dz (pooled row for DYPOOL)
 };
 template <int AKIND>
 __device__ __forceinline__ IssueCtx issue_ctx(const pn2_rows &s, int row) {
   IssueCtx c;
   c.valid = row < s.rows;
-  c.off = 0; c.goff = 0;
+  c.px = s.x; c.pd = s.dz;
   if (!c.valid) return c;
   if (AKIND == PN2_ROWS_GATHER) {
     const int cloud = row / (s.npoint * s.nsample);
-    c.off = (static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row)) * s.ld;
+    c.px = s.x + (static_cast<size_t>(cloud) * s.n_src + __ldg(s.idx + row)) * s.ld;
   } else {
-    c.off = static_cast<size_t>(row) * s.ld;
-    if (AKIND == PN2_ROWS_DYPOOL) c.goff = static_cast<size_t>(row / s.group) * s.ld;
+    c.px = s.x + static_cast<size_t>(row) * s.ld;
+    if (AKIND == PN2_ROWS_DY) c.pd = s.dz + static_cast<size_t>(row) * s.ld;
+    if (AKIND == PN2_ROWS_DYPOOL) c.pd = s.dz + static_cast<size_t>(row / s.group) * s.ld;
   }
   return c;
 }
@@ -761,7 +791,10 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
           if (it >= NB) mbar_wait_guarded(&empty_b[s], ((it / NB) - 1) & 1);  // the MMAs that read this stage are done
           if (kb == 0) tile_stamp(ti, 7);
           mbar_expect_tx(&full_b[s], BST);
-          bulk_g2s(ring_b + s * BST, b_src + static_cast<size_t>(kb) * (BST / 4), BST, &full_b[s]);
+          constexpr int PIECE = 16384;  // several bulk copies in flight per stage instead of one 32 / 64 KB copy
+#pragma unroll
+          for (int q = 0; q < BST / PIECE; ++q)
+            bulk_g2s(ring_b + s * BST + q * PIECE, b_src + static_cast<size_t>(kb) * (BST / 4) + q * (PIECE / 4), PIECE, &full_b[s]);
         }
       }
     }
@@ -770,11 +803,9 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
     // instruction chain: with 18 warps per SM a warp issues a dependent instruction every ~5 cycles, and this loop
     // (ring top-up, two barrier waits, shared-memory reads, transform, tcgen05.st + wait, fence + arrive) needs
     // ~1800 cycles per k-block although a thread only moves 8 values (profiles/r2_tile_trace.txt).  Ring positions and
-    // phase bits are carried incrementally instead of computed.  kPair = true handles TWO k-blocks per iteration (half
-    // the barrier round trips per k-block); measured SLOWER (63.9 vs 49.1 us on 32768 x 256 -> 256: the MMA warp then
-    // receives its stages in bursts), so it stays off -- as does a variant with four warp groups owning every fourth
-    // k-block (2.6 us per group and k-block).  See DESIGN.md section 4 for what this leaves on the table.
-    constexpr bool kPair = false;
+    // phase bits are carried incrementally instead of computed.  Rejected variants: TWO k-blocks per iteration (half
+    // the barrier round trips per k-block; 63.9 vs 49.1 us on 32768 x 256 -> 256: the MMA warp then receives its stages
+    // in bursts) and four warp groups owning every fourth k-block (2.6 us per group and k-block).
     // issue mapping: 16-byte chunk `chunk` of rows rsub, rsub + 64 (8 consecutive lanes = one 128-byte row segment)
     const int chunk = tid & 7, rsub = tid >> 3;
     // transform mapping: tile row 32*(warp%4) + lane (= this thread's TMEM lane), k columns 8*(warp/4) .. +7
@@ -783,7 +814,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
     const bool xyz_mine = AKIND == PN2_ROWS_GATHER && ((g.A.feat_cols % TK) / 8) == cgrp;
     const void *dummy = g.b_img;  // a valid address for zero-filling copies (src size 0 reads nothing)
     // per-thread constants of the two mappings
-    const uint32_t ring_r_s = smem_addr(ring_r);
+    const uint32_t ring_r_s = smem_addr(ring_r), coef_s = smem_addr(coef_a);
     uint32_t ioff[2];   // issue: byte offset of (row rsub + 64 i, chunk) inside a raw x / dz tile
 #pragma unroll
     for (int i = 0; i < 2; ++i) ioff[i] = (rsub + 64 * i) * 128 + ((chunk ^ ((rsub + 64 * i) & 7)) << 4);
@@ -791,10 +822,11 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) coff[j] = crow * 128 + (((2 * cgrp + j) ^ (crow & 7)) << 4);
 
-    // ring cursors, carried incrementally: slot index, phase parity of the slot's CURRENT use, "has wrapped" flag
+    // ring cursors, carried incrementally: slot index and phase parity of the slot's CURRENT use.  A first-time wait for
+    // "the previous use of this slot is over" asks for the phase before the barrier's first one, which reads as complete.
     int c_sr = 0, c_pr = 0;               // consume side of the raw ring
-    int c_sa = 0, c_pa = 0, c_la = 0;     // A stages in tensor memory
-    int i_sr = 0, i_pr = 0, i_lr = 0;     // issue side of the raw ring
+    int c_sa = 0, c_pa = 0;               // A stages in tensor memory
+    int i_sr = 0, i_pr = 0;               // issue side of the raw ring
     int il = 0, it = 0;                   // stream indices: next k-block to issue / to transform
     int lt = 0, lkb = 0;                  // the load cursor's tile sequence number and k-block inside that tile
     IssueCtx lc[2], nlc[2];               // issue contexts of the current tile / of the tile after it
@@ -809,26 +841,26 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
         cc = cons_ctx<AKIND>(g.A, m0 + crow, xyz_mine);
       }
     }
+    const int a_cols = AKIND == PN2_ROWS_GATHER ? g.A.feat_cols : g.A.cols;
     auto issue = [&](const IssueCtx (&c)[2], int kb) {  // this thread's copies of k-block kb into raw stage i_sr
-      if (i_lr) mbar_wait_guarded(&raw_empty[i_sr], i_pr ^ 1);
+      mbar_wait_guarded(&raw_empty[i_sr], i_pr ^ 1);
       const uint32_t raw = ring_r_s + i_sr * Cfg::kRawBytes;
       const int c4 = kb * TK + chunk * 4;
-      const bool col_ok = c4 < (AKIND == PN2_ROWS_GATHER ? g.A.feat_cols : g.A.cols);
+      const bool col_ok = c4 < a_cols;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const bool ok = c[i].valid && col_ok;
         const int nb = ok ? 16 : 0;
-        cp_async16(raw + ioff[i], ok ? static_cast<const void *>(g.A.x + c[i].off + c4) : dummy, nb);
+        cp_async16(raw + ioff[i], ok ? static_cast<const void *>(c[i].px + c4) : dummy, nb);
         if (Cfg::kDz) {
-          const size_t doff = (AKIND == PN2_ROWS_DYPOOL ? c[i].goff : c[i].off) + c4;
-          cp_async16(raw + TILE_BYTES + ioff[i], ok ? static_cast<const void *>(g.A.dz + doff) : dummy, nb);
+          cp_async16(raw + TILE_BYTES + ioff[i], ok ? static_cast<const void *>(c[i].pd + c4) : dummy, nb);
           if (Cfg::kArg)
-            cp_async4(raw + 2 * TILE_BYTES + (chunk * TM + rsub + 64 * i) * 4, ok ? static_cast<const void *>(g.A.arg + doff) : dummy,
-                      ok ? 4 : 0);
+            cp_async4(raw + 2 * TILE_BYTES + (chunk * TM + rsub + 64 * i) * 4,
+                      ok ? static_cast<const void *>(g.A.arg + (c[i].pd - g.A.dz) + c4) : dummy, ok ? 4 : 0);
         }
       }
       cp_async_arrive(&raw_full[i_sr]);
-      if (++i_sr == NR) { i_sr = 0; i_pr ^= 1; i_lr = 1; }
+      if (++i_sr == NR) { i_sr = 0; i_pr ^= 1; }
       ++il;
       if (++lkb == num_kb) { lkb = 0; ++lt; }
     };
@@ -856,72 +888,49 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
       }
       RowCtx rc;
       rc.valid = cc.valid; rc.off = 0; rc.goff = 0; rc.slot = cc.slot; rc.gx = cc.gx; rc.gy = cc.gy; rc.gz = cc.gz;
-      for (int kb = 0; kb < num_kb; kb += kPair ? 2 : 1) {
-        const bool two = kPair && kb + 1 < num_kb;  // warp-uniform: a pair, or a single k-block
-        // 1. keep the raw ring full: up to NR - 1 k-blocks beyond the first one of this pair, into the next tile if need be
+      for (int kb = 0; kb < num_kb; ++kb) {
+        // 1. keep the raw ring full: up to NR - 1 k-blocks beyond this one, into the next tile if need be
         while (il - it < NR - 1) {
           if (lt == ti) issue(lc, lkb);
           else if (lt == ti + 1 && have_next) issue(nlc, lkb);
           else break;
         }
-        // 2. the pair's raw stages have landed (all 512 threads' copies): read this thread's pieces, release the stages
-        const int sr0 = c_sr, pr0 = c_pr;
-        if (++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
-        const int sr1 = c_sr, pr1 = c_pr;
-        if (two && ++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
-        Raw rw[2][2];
-        mbar_wait_guarded(&raw_full[sr0], pr0);
-        if (two) mbar_wait_guarded(&raw_full[sr1], pr1);
+        // 2. the raw stage has landed (all 512 threads' copies): read this thread's pieces, release the stage
+        mbar_wait_guarded(&raw_full[c_sr], c_pr);
+        const uint32_t raw = ring_r_s + c_sr * Cfg::kRawBytes;
+        Raw rw[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const unsigned char *raw = ring_r + (u ? sr1 : sr0) * Cfg::kRawBytes;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            rw[u][j].x = zero4(); rw[u][j].d = zero4(); rw[u][j].a = make_uchar4(0, 0, 0, 0);
-            if (u == 0 || two) {
-              rw[u][j].x = lds4(raw + coff[j]);
-              if (Cfg::kDz) rw[u][j].d = lds4(raw + TILE_BYTES + coff[j]);
-              if (Cfg::kArg) rw[u][j].a = *reinterpret_cast<const uchar4 *>(raw + 2 * TILE_BYTES + ((2 * cgrp + j) * TM + crow) * 4);
-            }
+        for (int j = 0; j < 2; ++j) {
+          rw[j].x = lds_v4(raw + coff[j]);
+          rw[j].d = zero4(); rw[j].a = make_uchar4(0, 0, 0, 0);
+          if (Cfg::kDz) rw[j].d = lds_v4(raw + TILE_BYTES + coff[j]);
+          if (Cfg::kArg) {
+            const uint32_t a = lds_u32(raw + 2 * TILE_BYTES + ((2 * cgrp + j) * TM + crow) * 4);
+            rw[j].a = make_uchar4(a & 0xff, (a >> 8) & 0xff, (a >> 16) & 0xff, a >> 24);
           }
         }
         __syncwarp();
-        if (lane == 0) {  // the stages may be refilled once all 16 warps have read them
-          mbar_arrive(&raw_empty[sr0]);
-          if (two) mbar_arrive(&raw_empty[sr1]);
-        }
+        if (lane == 0) mbar_arrive(&raw_empty[c_sr]);  // the stage may be refilled once all 16 warps have read it
+        if (++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
         // 3. transform + split
-        float hi[2][8], lo[2][8];
+        float hi[8], lo[8];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float4 v = apply_raw<AKIND>(g.A, rc, (kb + u) * TK + cgrp * 8 + 4 * j, rw[u][j], coef_a, Cfg::kCoefK, 0);
-            split_tf32(v.x, hi[u][4 * j + 0], lo[u][4 * j + 0]); split_tf32(v.y, hi[u][4 * j + 1], lo[u][4 * j + 1]);
-            split_tf32(v.z, hi[u][4 * j + 2], lo[u][4 * j + 2]); split_tf32(v.w, hi[u][4 * j + 3], lo[u][4 * j + 3]);
-          }
-        // 4. straight into tensor memory: the A stages of the pair are free once the MMAs that read them have completed
-        const int sa0 = c_sa, pa0 = c_pa, la0 = c_la;
-        if (++c_sa == NA) { c_sa = 0; c_pa ^= 1; c_la = 1; }
-        const int sa1 = c_sa, pa1 = c_pa, la1 = c_la;
-        if (two && ++c_sa == NA) { c_sa = 0; c_pa ^= 1; c_la = 1; }
-        if (la0) mbar_wait_guarded(&empty_a[sa0], pa0 ^ 1);
-        if (two && la1) mbar_wait_guarded(&empty_a[sa1], pa1 ^ 1);
-        if (la0 || la1) tc_fence_after_sync();
-        tmem_st8(lane_base + sa0 * AS_A_STAGE_COLS, hi[0]);
-        tmem_st8(lane_base + sa0 * AS_A_STAGE_COLS + 32, lo[0]);
-        if (two) {
-          tmem_st8(lane_base + sa1 * AS_A_STAGE_COLS, hi[1]);
-          tmem_st8(lane_base + sa1 * AS_A_STAGE_COLS + 32, lo[1]);
+        for (int j = 0; j < 2; ++j) {
+          const float4 v = apply_raw_s<AKIND>(g.A, rc, kb * TK + cgrp * 8 + 4 * j, rw[j], coef_s, Cfg::kCoefK);
+          split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
         }
+        // 4. straight into tensor memory: the A stage is free once the MMAs that read it have completed
+        mbar_wait_guarded(&empty_a[c_sa], c_pa ^ 1);
+        tc_fence_after_sync();
+        tmem_st8(lane_base + c_sa * AS_A_STAGE_COLS, hi);
+        tmem_st8(lane_base + c_sa * AS_A_STAGE_COLS + 32, lo);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&full_a[sa0]);
-          if (two) mbar_arrive(&full_a[sa1]);
-        }
-        it += two ? 2 : 1;
+        if (lane == 0) mbar_arrive(&full_a[c_sa]);
+        if (++c_sa == NA) { c_sa = 0; c_pa ^= 1; }
+        ++it;
         if (tid == 0 && kb == 0) tile_stamp(ti, 1);
       }
       if (tid == 0) {
@@ -989,6 +998,353 @@ int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
   return launch_tc_async_w<AKIND, EPI, 128>(g, stream);
 }
 
+// ---- weight-gradient kernel: async raw ring, thread = channel ---------------------------------------------------------
+// dW[cout tile 128][cin tile 128] over a slice of positions (blockIdx.z).  K runs over POSITIONS, and both operands are row
+// sources with the channels contiguous, so the operand tiles are the TRANSPOSE of what arrives from memory.
+// gemm_tc_kernel<TRANS> above does that transposition with MN-major tiles staged through registers, one k-block of
+// prefetch deep: 2.8 us per 32-position k-block where the 48 KB it reads cost ~1 us of the SM's share of HBM.  Here:
+//   * raw ring (3 stages): per k-block the 32 positions x 128 channels of  y | dz | activation  (+ the pooled arg-max
+//     bytes, + the neighbour / centre coordinates of a gathered source) are copied by cp.async exactly as they lie in
+//     memory -- a warp copies one position's 512 contiguous bytes -- with completion on an mbarrier; two k-blocks
+//     (96 KB) are in flight per SM beyond the one being transformed;
+//   * transform with thread = CHANNEL (32 * (warp % 4) + lane) for 8 positions (8 * (warp / 4) ..): the 4-byte reads of
+//     a warp are 32 consecutive words of one position row (conflict-free without a swizzle), the per-channel BatchNorm
+//     coefficients live in registers, and the thread's 8 values are 8 consecutive K elements of ITS row of the operand:
+//     dY goes straight into tensor memory (tcgen05.st, lane = channel), the activation into a K-major 128-byte-swizzle
+//     tile with four 16-byte stores -- the same operand forms as the forward kernel, no MN-major descriptors;
+//   * the MMA warp (converged, elect.sync) issues the 12 TS-form MMAs of a k-block; 2 operand stages.
+struct IncDiv {  // quotient of a position that advances by a fixed step per k-block, without dividing
+  int q, rem, d, dq, dr;
+  __device__ __forceinline__ void init(int r, int d_, int step) {
+    d = d_ > 0 ? d_ : 1;
+    q = r / d; rem = r - q * d;
+    dq = step / d; dr = step - dq * d;
+  }
+  __device__ __forceinline__ void advance() {
+    q += dq; rem += dr;
+    if (rem >= d) { rem -= d; ++q; }
+  }
+  __device__ __forceinline__ int q_at(int delta) const {  // quotient `delta` (small) positions further on
+    int qq = q, rr = rem + delta;
+    while (rr >= d) { rr -= d; ++qq; }
+    return qq;
+  }
+};
+
+template <int AKIND, int BKIND>
+struct WgCfg {
+  static constexpr bool kArg = AKIND == PN2_ROWS_DYPOOL;
+  static constexpr bool kXyz = BKIND == PN2_ROWS_GATHER;
+  static constexpr int kOffB = 2 * TILE_BYTES;                     // raw stage: y | dz | activation | arg | xyz
+  static constexpr int kOffArg = 3 * TILE_BYTES;
+  static constexpr int kOffXyz = kOffArg + (kArg ? TK * TM : 0);
+  static constexpr int kRawBytes = kOffXyz + (kXyz ? 1024 : 0);    // [6][32] floats: neighbour xyz, centre xyz
+  static constexpr int kNR = 3, kNS = 2;
+  // A gathered source whose feature width is a multiple of 128 puts its 4-column xyz block into an n-tile of its own, which
+  // cost a full share of the CTAs for 3 useful channels (kp = 260: 6 tiles instead of 4).  Folded: the LAST feature tile
+  // runs its MMAs with N = 144 and carries the xyz channels as operand rows 128..130 (rows 131..143 stay zero).
+  static constexpr bool kFoldable = kXyz && !kArg;
+  static constexpr int kOpTile = kFoldable ? 18 * 1024 : TILE_BYTES;  // one half (hi or lo) of an activation operand stage
+  static constexpr int kACol0 = kFoldable ? 160 : TN;                // first dY column in tensor memory (accumulator below)
+  static constexpr uint32_t kTmemCols = kFoldable ? 512 : 256;       // accumulator + 2 dY stages of 32 hi + 32 lo columns
+  static constexpr int kOps = kNS * 2 * kOpTile;                     // activation operand stages: hi | lo
+  static constexpr int kRing = kOps + kNR * kRawBytes;
+  static constexpr int kSmem = kRing + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kSmem <= 232448, "shared memory budget");
+  static_assert(kRing >= (TC_THREADS / 32) * 32 * 36 * 4 + 4096, "epilogue scratch aliases the rings");
+};
+template <int AKIND, int BKIND>
+__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
+wgrad_tc_async_kernel(const __grid_constant__ GemmArgs g) {
+  using Cfg = WgCfg<AKIND, BKIND>;
+  constexpr int NR = Cfg::kNR, NS = Cfg::kNS;
+  pdl_prologue();
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char *ops = tiles, *ring_r = tiles + Cfg::kOps;
+  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + Cfg::kRing);  // operand stage written (16 warps)
+  uint64_t *empty = full + NS;                                        // its MMAs done
+  uint64_t *raw_full = empty + NS, *raw_empty = raw_full + NR;        // raw stage landed (512 async arrivals) / read (16 warps)
+  uint64_t *done_bar = raw_empty + NR;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  static_assert((2 * NS + 2 * NR + 1) * 8 + 4 <= 256, "barrier block");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp < TC_THREADS / 32;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const bool fold = Cfg::kFoldable && g.wg_fold && n0 + TN == g.B.feat_cols;  // this tile carries the xyz block as well
+  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int k_begin = blockIdx.z * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
+  const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
+  trace_stamp(g, cta_id, 0, smid());
+  trace_stamp(g, cta_id, 1, globaltimer_ns());
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], TC_THREADS / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], TC_THREADS); mbar_init(&raw_empty[s], TC_THREADS / 32); }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (fold && producer)  // operand rows 128..143 of every stage half: zero, rows 128..130 are rewritten per k-block
+    for (int i = tid; i < NS * 2 * 128; i += TC_THREADS)
+      *reinterpret_cast<float4 *>(ops + (i >> 7) * Cfg::kOpTile + 16 * 1024 + (i & 127) * 16) = zero4();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = fold ? idesc_tf32(TM, TN + 16, false) : idesc_tf32(TM, TN, false);
+  trace_stamp(g, cta_id, 2, globaltimer_ns());
+
+  if (!producer) {  // ---- MMA warp, converged
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % NS;
+      mbar_wait_guarded(&full[s], (kb / NS) & 1);
+      tc_fence_after_sync();
+      const uint32_t a_hi = tmem_u + Cfg::kACol0 + s * 64, a_lo = a_hi + 32;
+      const uint32_t bbase = smem_addr(ops + s * 2 * Cfg::kOpTile);
+      const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + Cfg::kOpTile);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint64_t adv = static_cast<uint64_t>(2 * ks);
+          mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
+          mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_lo + adv, idesc, true);
+          mma_tf32_ts(tmem_u, a_lo + 8 * ks, b_hi + adv, idesc, true);
+        }
+        mma_commit(&empty[s]);
+        if (kb == num_kb - 1) mma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // transform mapping: channel ch of both 128-channel tiles (= this thread's TMEM lane), positions 8 pg .. 8 pg + 7
+    const int quarter = warp & 3, pg = warp >> 2, ch = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + Cfg::kACol0 + pg * 8;
+    uint32_t boff[2];  // activation operand: 16-byte chunks 2 pg, 2 pg + 1 of row ch
+#pragma unroll
+    for (int j = 0; j < 2; ++j) boff[j] = sw128_offset(ch, 2 * pg + j);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f;  // per-channel coefficients of the two sources
+    if (m0 + ch < g.A.cols) {
+      a0 = __ldg(g.A.c0 + m0 + ch); a1 = __ldg(g.A.c1 + m0 + ch); a2 = __ldg(g.A.c2 + m0 + ch);
+    }
+    if (BKIND == PN2_ROWS_BNRELU && n0 + ch < g.B.cols) {
+      b0 = __ldg(g.B.c0 + n0 + ch); b1 = __ldg(g.B.c1 + n0 + ch);
+    }
+    const int xd = n0 + ch - g.B.feat_cols;  // gathered source: 0..2 = this thread produces a local coordinate
+    const bool xyz_mine = Cfg::kXyz && g.B.use_xyz && xd >= 0 && xd < 3;
+    const bool xyz_tile = Cfg::kXyz && g.B.use_xyz && ((g.B.feat_cols >= n0 && g.B.feat_cols < n0 + TN) || fold);
+    // issue mapping: 16-byte chunk `lane` (channels 4 lane ..) of positions warp, warp + 16
+    const void *dummy = g.A.x;  // a valid address for zero-filling copies (src size 0 reads nothing)
+    const uint32_t ring_r_s = smem_addr(ring_r);
+    const bool col_a = m0 + 4 * lane < g.A.cols;
+    const bool col_b = n0 + 4 * lane < (BKIND == PN2_ROWS_GATHER ? g.B.feat_cols : g.B.cols);
+    int i_sr = 0, i_pr = 0, il = 0;
+    int c_sr = 0, c_pr = 0;
+    // positions advance by 32 per k-block: centre (r / nsample), cloud (r / (npoint nsample)) and pooled row (r / group)
+    // are carried incrementally -- three integer divisions per position and k-block were a third of this loop
+    IncDiv d_centre, d_cloud, d_group;
+    d_centre.init(k_begin + warp, BKIND == PN2_ROWS_GATHER ? g.B.nsample : 1, TK);
+    d_cloud.init(k_begin + warp, BKIND == PN2_ROWS_GATHER ? g.B.npoint * g.B.nsample : 1, TK);
+    d_group.init(k_begin + warp, AKIND == PN2_ROWS_DYPOOL ? g.A.group : 1, TK);
+    // this thread's 16 bytes of position k_begin + warp in each source (the second copy is 16 rows further on), advanced by
+    // 32 rows per k-block
+    const size_t lda = static_cast<size_t>(g.A.ld), ldb = static_cast<size_t>(g.B.ld);
+    const size_t row0 = static_cast<size_t>(k_begin + warp);
+    const float *pax = g.A.x + row0 * lda + m0 + 4 * lane;
+    const float *pad = g.A.dz + (AKIND == PN2_ROWS_DYPOOL ? 0 : row0 * lda) + m0 + 4 * lane;
+    const float *pbx = g.B.x + (BKIND == PN2_ROWS_GATHER ? 0 : row0 * ldb) + n0 + 4 * lane;
+    int r0 = k_begin + warp;
+    int nidx[2] = {0, 0};
+    auto load_idx = [&](int kb) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = k_begin + kb * TK + warp + 16 * i;
+        nidx[i] = (BKIND == PN2_ROWS_GATHER && kb < num_kb && r < k_end) ? __ldg(g.B.idx + r) : 0;
+      }
+    };
+    load_idx(0);
+    auto issue = [&](int kb) {  // this thread's copies of k-block kb into raw stage i_sr
+      const int idx_now[2] = {nidx[0], nidx[1]};
+      load_idx(kb + 1);  // consumed by the next call: the index load and the copies that depend on it never meet
+      mbar_wait_guarded(&raw_empty[i_sr], i_pr ^ 1);  // (first use: the phase before the barrier's first reads as complete)
+      const uint32_t raw = ring_r_s + i_sr * Cfg::kRawBytes;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int p = warp + 16 * i;
+        const bool rv = r0 + 16 * i < k_end;
+        const uint32_t dst = raw + p * 512 + lane * 16;
+        const bool oka = rv && col_a;
+        const float *ax = pax + (i ? 16 * lda : 0);
+        const float *ad = AKIND == PN2_ROWS_DYPOOL ? pad + static_cast<size_t>(i ? d_group.q_at(16) : d_group.q) * lda
+                                                   : pad + (i ? 16 * lda : 0);
+        cp_async16(dst, oka ? static_cast<const void *>(ax) : dummy, oka ? 16 : 0);
+        cp_async16(dst + TILE_BYTES, oka ? static_cast<const void *>(ad) : dummy, oka ? 16 : 0);
+        if (Cfg::kArg) {
+          const unsigned char *aa = g.A.arg + (ad - g.A.dz);
+          cp_async4(raw + Cfg::kOffArg + p * TM + lane * 4, oka ? static_cast<const void *>(aa) : dummy, oka ? 4 : 0);
+        }
+        size_t src = 0;
+        const float *bx = pbx + (i ? 16 * ldb : 0);
+        if (BKIND == PN2_ROWS_GATHER) {
+          src = static_cast<size_t>(i ? d_cloud.q_at(16) : d_cloud.q) * g.B.n_src + idx_now[i];
+          bx = pbx + src * ldb;
+        }
+        const bool okb = rv && col_b;
+        cp_async16(dst + Cfg::kOffB, okb ? static_cast<const void *>(bx) : dummy, okb ? 16 : 0);
+        if (Cfg::kXyz && xyz_tile && lane < 6) {
+          const float *q = lane < 3 ? g.B.xyz + src * 3 + lane
+                                    : g.B.centres + static_cast<size_t>(i ? d_centre.q_at(16) : d_centre.q) * 3 + (lane - 3);
+          cp_async4(raw + Cfg::kOffXyz + (lane * 32 + p) * 4, rv ? static_cast<const void *>(q) : dummy, rv ? 4 : 0);
+        }
+      }
+      r0 += TK;
+      pax += TK * lda;
+      if (AKIND != PN2_ROWS_DYPOOL) pad += TK * lda;
+      if (BKIND != PN2_ROWS_GATHER) pbx += TK * ldb;
+      cp_async_arrive(&raw_full[i_sr]);
+      if (++i_sr == NR) { i_sr = 0; i_pr ^= 1; }
+      ++il;
+      if (BKIND == PN2_ROWS_GATHER) { d_centre.advance(); d_cloud.advance(); }
+      if (AKIND == PN2_ROWS_DYPOOL) d_group.advance();
+    };
+
+    int slot_pg = AKIND == PN2_ROWS_DYPOOL ? (k_begin + pg * 8) % g.A.group : 0;  // pool slot of this thread's first position
+    const int slot_step = AKIND == PN2_ROWS_DYPOOL ? TK % g.A.group : 0;
+    // the three local-coordinate rows of a gathered source are produced by warps 0..2, lane = position (ONE correctly
+    // rounded division per thread; eight per thread in the channel mapping made those warps the tail of every k-block)
+    const bool xyz_warp = xyz_tile && warp < 3;
+    const uint32_t xoff = sw128_offset(fold ? TN + warp : g.B.feat_cols - n0 + warp, lane >> 2) + (lane & 3) * 4;
+    // An operand stage is SIGNALLED one iteration late: tcgen05.wait::st and the async-proxy fence then find their stores
+    // long complete instead of stalling all 16 warps (which run in lock-step) at the end of every k-block.
+    auto signal = [&](int s) {
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    };
+    for (int kb = 0; kb < num_kb; ++kb) {
+      // 1. keep the raw ring full: the block about to be read + NR - 1 behind it
+      while (il < num_kb && il - kb < NR) issue(il);
+      // 2. this k-block has landed (all 512 threads' copies): read this thread's channel of 8 positions, release the stage
+      mbar_wait_guarded(&raw_full[c_sr], c_pr);
+      const uint32_t rbase = ring_r_s + c_sr * Cfg::kRawBytes;
+      const uint32_t rmine = rbase + pg * 8 * 512 + ch * 4;  // this thread's channel of its first position
+      const int nvalid = k_end - (k_begin + kb * TK + pg * 8);  // < 8 only in the last k-block of a slice
+      float y[8], dz[8], xb[8];
+      int slot = slot_pg;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = lds_f32(rmine + j * 512);
+        dz[j] = lds_f32(rmine + TILE_BYTES + j * 512);
+        xb[j] = lds_f32(rmine + Cfg::kOffB + j * 512);
+        if (Cfg::kArg) {
+          const int a = lds_u8(rbase + Cfg::kOffArg + pg * 8 * TM + ch + j * TM);
+          dz[j] = a == slot ? dz[j] : 0.f;
+          if (++slot == g.A.group) slot = 0;
+        }
+      }
+      if (Cfg::kArg) {
+        slot_pg += slot_step;
+        if (slot_pg >= g.A.group) slot_pg -= g.A.group;
+      }
+      float xv = 0.f;
+      if (Cfg::kXyz && xyz_warp) {  // pointnet2_utils.py:350-352: grouped_xyz -= new_xyz; grouped_xyz /= radius
+        const uint32_t rx = rbase + Cfg::kOffXyz + (warp * 32 + lane) * 4;
+        xv = __fdiv_rn(__fsub_rn(lds_f32(rx), lds_f32(rx + 3 * 32 * 4)), g.B.inv_scale);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[c_sr]);
+      if (++c_sr == NR) { c_sr = 0; c_pr ^= 1; }
+      // 3. hand the PREVIOUS k-block's operand stage to the MMA warp; this one's stage is free once the MMAs that read
+      //    it (k-block kb - NS) have completed
+      const int s = kb % NS;
+      if (kb > 0) signal((kb - 1) % NS);
+      mbar_wait_guarded(&empty[s], ((kb / NS) & 1) ^ 1);
+      tc_fence_after_sync();
+      // 4. dY = c0 dz + c1 + c2 y  -> tensor memory (positions past the slice contribute nothing: dY = 0 there)
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(a2, y[j], fmaf(a0, dz[j], a1));
+      if (nvalid < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = j < nvalid ? y[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_tf32(y[j], hi[j], lo[j]);
+      tmem_st8(lane_base + s * 64, hi);
+      tmem_st8(lane_base + s * 64 + 32, lo);
+      // 5. activation -> K-major operand tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = xb[j];
+        if (BKIND == PN2_ROWS_BNRELU) v = relu_nan(fmaf(v, b0, b1));
+        split_tf32(v, hi[j], lo[j]);
+      }
+      unsigned char *st = ops + s * 2 * Cfg::kOpTile;
+      if (!xyz_mine) {  // (a local-coordinate row belongs to its warp below)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          *reinterpret_cast<float4 *>(st + boff[j]) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<float4 *>(st + Cfg::kOpTile + boff[j]) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      if (Cfg::kXyz && xyz_warp) {
+        float h, l;
+        split_tf32(xv, h, l);
+        *reinterpret_cast<float *>(st + xoff) = h;
+        *reinterpret_cast<float *>(st + Cfg::kOpTile + xoff) = l;
+      }
+    }
+    if (num_kb > 0) signal((num_kb - 1) % NS);
+    float4 yv[8];
+    tc_epilogue_prefetch<TC_EPI_STORE>(g, m0, n0, yv);
+    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
+    tc_fence_after_sync();
+    trace_stamp(g, cta_id, 3, globaltimer_ns());
+    if (Cfg::kFoldable && fold && pg == 0 && num_kb > 0) {  // accumulator columns 128..130: the xyz block's gradient
+      float v[32];
+      tmem_ld32(tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + TN, v);
+      if (m0 + ch < g.M)
+        *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(m0 + ch) * g.ldo + n0 + TN) =
+            make_float4(v[0], v[1], v[2], v[3]);
+    } else if (Cfg::kFoldable && fold && pg == 0 && m0 + ch < g.M) {
+      *reinterpret_cast<float4 *>(g.out + blockIdx.z * g.out_split_stride + static_cast<size_t>(m0 + ch) * g.ldo + n0 + TN) = zero4();
+    }
+    float(&red)[2][TC_THREADS / 32][32] =
+        *reinterpret_cast<float(*)[2][TC_THREADS / 32][32]>(tiles + (TC_THREADS / 32) * 32 * 36 * 4);  // unused by EPI_STORE
+    tc_epilogue<TC_EPI_STORE>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0, yv);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::kTmemCols>(tmem_d);
+  trace_stamp(g, cta_id, 4, globaltimer_ns());
+  trace_stamp(g, cta_id, 5, static_cast<unsigned long long>(num_kb));
+}
+
+template <int AKIND, int BKIND>
+int launch_wgrad_async(const GemmArgs &g, int splits, cudaStream_t stream) {
+  using Cfg = WgCfg<AKIND, BKIND>;
+  auto kernel = wgrad_tc_async_kernel<AKIND, BKIND>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    configured_dev = dev;
+  }
+  dim3 grid((g.M + TM - 1) / TM, g.wg_fold ? g.B.feat_cols / TN : (g.N + TN - 1) / TN, splits);
+  if (g.wg_fold && !Cfg::kFoldable) return PN2_TC_UNSUPPORTED;  // the caller asks wgrad_fold_ok() first
+  GemmArgs a = g;
+  gemm_trace_target(&a.trace, &a.trace_cap);
+  pn2::launch(kernel, grid, dim3(TC_CTA_THREADS), Cfg::kSmem, stream, a);
+  return check_launch("wgrad_tc_async_kernel");
+}
+
 template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
 int launch_tc_rot(const GemmArgs &g, int splits, cudaStream_t stream) {
   auto kernel = gemm_tc_kernel<AKIND, BKIND, TRANS, EPI, ROT>;
@@ -1021,6 +1377,18 @@ static int g_trace_cap = 0;
 void gemm_trace_target(unsigned long long **buf, int *cap) {
   *buf = g_trace_buf;
   *cap = g_trace_cap;
+}
+
+// xyz block of a gathered source folded into the last feature tile of the weight-gradient kernel (WgCfg::kFoldable)
+bool wgrad_fold_ok(const void *gemm_args) {
+  static const bool on = [] {
+    const char *e = getenv("PN2_WGRAD_FOLD");
+    const char *a = getenv("PN2_WGRAD_ASYNC");
+    return (e == nullptr || e[0] != '0') && (a == nullptr || a[0] != '0');
+  }();
+  const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
+  return on && gemm_tc_enabled() && g.A.kind == PN2_ROWS_DY && g.B.kind == PN2_ROWS_GATHER && g.B.use_xyz && g.B.feat_cols >= TN &&
+         g.B.feat_cols % TN == 0 && g.B.cols == g.B.feat_cols + 4;
 }
 
 bool gemm_tc_wide_enabled() {
@@ -1067,8 +1435,13 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled()) return PN2_TC_UNSUPPORTED;
-#define PN2_TC_W(AK, BK) \
-  if (g.A.kind == AK && g.B.kind == BK) return launch_tc<AK, BK, true, TC_EPI_STORE>(g, splits, stream);
+  static const bool async_on = [] {  // PN2_WGRAD_ASYNC=0: the register-staged MN-major kernel (A/B comparisons)
+    const char *e = getenv("PN2_WGRAD_ASYNC");
+    return e == nullptr || e[0] != '0';
+  }();
+#define PN2_TC_W(AK, BK)                                                \
+  if (g.A.kind == AK && g.B.kind == BK)                                 \
+    return async_on ? launch_wgrad_async<AK, BK>(g, splits, stream) : launch_tc<AK, BK, true, TC_EPI_STORE>(g, splits, stream);
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_PLAIN)
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_BNRELU)
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_GATHER)

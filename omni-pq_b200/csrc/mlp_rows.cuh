@@ -107,6 +107,7 @@ struct GemmArgs {
   unsigned long long *trace;
   int trace_cap;
   int *tile_counter;  // persistent GEMM: dynamic tile scheduler (self-resetting ticket counter)
+  int wg_fold;        // weight gradient: the gathered source's xyz block rides in the last feature tile (wgrad_fold_ok)
 };
 
 }  // namespace
@@ -116,6 +117,7 @@ constexpr int PN2_TC_UNSUPPORTED = -100;
 int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t stream);
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream);
 bool gemm_tc_enabled();
+bool wgrad_fold_ok(const void *gemm_args);  // weight gradient of a gathered source: xyz block folded into the last feature tile
 bool gemm_tc_wide_enabled();  // PN2_TC_WIDE=0: 128 x 128 tiles (and weight images) everywhere
 void gemm_trace_target(unsigned long long **buf, int *cap);
 

@@ -172,12 +172,14 @@ __device__ __forceinline__ bool elect_one() {
 // TRUNCATES fp32 operands to tf32; an unrounded remainder would lose up to 2^-22 |v| in one direction on every
 // element -- a bias that adds up linearly over K and put the 3xTF32 GEMM at ~1e-6 relative where fp32 FMA is at
 // 3e-7 (tests/arbiter.py).  Rounded, the error per operand is 2^-24 |v| with either sign.
+// Round-to-nearest (ties away from zero) to tf32 is done on the bit pattern, add half an ulp of the 10-bit mantissa and
+// clear the 13 dropped bits -- what cvt.rna.tf32.f32 computes for every finite value, in 2 instructions: ptxas expands
+// the cvt into ~7 (NaN / Inf handling), and at 2 cvt per operand element that was a quarter of the producers' k-block.
+// Inf stays Inf (lo = NaN), a NaN keeps a NaN in lo: either way the product is NaN, as with the cvt form.
+__device__ __forceinline__ float round_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  lo = __uint_as_float(l);
+  hi = round_tf32(v);
+  lo = round_tf32(v - hi);
 }
 
 }  // namespace sm100
