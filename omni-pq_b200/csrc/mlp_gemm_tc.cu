@@ -575,15 +575,19 @@ struct AsCfg {
   static constexpr bool kArg = AKIND == PN2_ROWS_DYPOOL;
   static constexpr bool kCoef = !(AKIND == PN2_ROWS_PLAIN || AKIND == PN2_ROWS_GATHER);
   static constexpr int kRawBytes = TILE_BYTES * (kDz ? 2 : 1) + (kArg ? AS_ARG_BYTES : 0);
-  static constexpr int kBStage = 2 * TNW * TK * 4;                              // weight stage: hi + lo, 32 / 64 KB
+  // weight ring: slots of one k-block x 128 output rows (hi 16 KB | lo 16 KB).  A 256-wide tile consumes two slots per
+  // k-block, each with its own barriers and its own six N = 128 MMA pairs: with whole 64 KB stages the ring was two deep
+  // and a k-block waited ~1.1 us for its weights where the MMAs need 0.78
+  static constexpr int kBSlot = 2 * TN * TK * 4;
+  static constexpr int kH = TNW / TN;                                           // slots per k-block
   static constexpr int kNR = kDz ? (TNW == 256 ? 2 : 3) : 5;                    // raw stages
-  static constexpr int kNB = TNW == 256 ? 2 : (kDz ? 3 : 4);                    // weight stages
+  static constexpr int kNB = TNW == 256 ? 4 : (kDz ? 3 : 4);                    // weight slots
   static constexpr int kNA = (static_cast<int>(AS_TMEM_COLS) - TNW) / static_cast<int>(AS_A_STAGE_COLS);  // A stages: 6 / 4
   static constexpr int kCoefK = kCoef ? 640 : 0;         // largest K with per-channel coefficient vectors (else FFMA kernel)
-  static constexpr int kRing = kNB * kBStage + kNR * kRawBytes;
+  static constexpr int kRing = kNB * kBSlot + kNR * kRawBytes;
   static constexpr int kSmem = kRing + 1024 /*align*/ + 512 /*barriers, tickets*/ + 3 * kCoefK * 4;
   static_assert(kSmem + 4096 /*static: statistics partials*/ <= 232448, "shared memory budget");
-  static_assert(kNB * kBStage >= (TC_THREADS / 32) * 32 * 36 * 4, "epilogue scratch aliases the weight ring");
+  static_assert(kNB * kBSlot >= (TC_THREADS / 32) * 32 * 36 * 4, "epilogue scratch aliases the weight ring");
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
@@ -689,12 +693,12 @@ __global__ void __launch_bounds__(AS_CTA_THREADS, 1)  // 96 registers: more (__m
 gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   using Cfg = AsCfg<AKIND, TNW>;
   constexpr int NR = Cfg::kNR, NB = Cfg::kNB, NA = Cfg::kNA;
-  constexpr int BST = Cfg::kBStage;
+  constexpr int BSL = Cfg::kBSlot, H = Cfg::kH;
   constexpr uint32_t AS_A_COL0 = TNW;
   pdl_prologue();
   extern __shared__ unsigned char smem_raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char *ring_b = tiles, *ring_r = tiles + NB * BST;
+  unsigned char *ring_b = tiles, *ring_r = tiles + NB * BSL;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + Cfg::kRing);
   uint64_t *full_b = bars, *empty_b = full_b + NB;            // weight stage landed / its MMAs done
   uint64_t *raw_full = empty_b + NB, *raw_empty = raw_full + NR;  // raw stage landed (512 async arrivals) / read (16 warps)
@@ -740,7 +744,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(TM, TNW, false);
+  const uint32_t idesc = idesc_tf32(TM, TN, false);
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
   if (!producer) {
@@ -750,51 +754,65 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
     if (warp == TC_THREADS / 32) {  // ---- MMA warp, converged: the k-blocks of all of this CTA's tiles form one stream `it`
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);  // warp-uniform for the compiler too
       int it = 0;
+      int qb = 0, pb = 0;  // weight-slot cursor: slot, phase parity of its current use
       for (int ti = 0;; ++ti) {
         mbar_wait_guarded(tile_bar, ti & 1);
         if (__shfl_sync(0xffffffffu, ticket[ti & 7], 0) >= ntiles) break;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int sa = it % NA, sb = it % NB;
+          const int sa = it % NA;
           mbar_wait_guarded(&full_a[sa], (it / NA) & 1);
           if (kb == 0 && lane == 0) tile_stamp(ti, 5);
-          mbar_wait_guarded(&full_b[sb], (it / NB) & 1);
-          tc_fence_after_sync();
-          if (kb == 0 && lane == 0) tile_stamp(ti, 6);
           const uint32_t a_hi = tmem_u + AS_A_COL0 + sa * AS_A_STAGE_COLS, a_lo = a_hi + 32;
-          const uint32_t bbase = smem_addr(ring_b + sb * BST);
-          const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + BST / 2);
-          if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TK / 8; ++ks) {
-              const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
-              mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
-              mma_tf32_ts(tmem_u, a_hi + 8 * ks, b_lo + adv, idesc, true);
-              mma_tf32_ts(tmem_u, a_lo + 8 * ks, b_hi + adv, idesc, true);
+          for (int h = 0; h < H; ++h) {
+            mbar_wait_guarded(&full_b[qb], pb);
+            tc_fence_after_sync();
+            if (kb == 0 && h == 0 && lane == 0) tile_stamp(ti, 6);
+            const uint32_t bbase = smem_addr(ring_b + qb * BSL);
+            const uint64_t b_hi = smem_desc_sw128(bbase), b_lo = smem_desc_sw128(bbase + BSL / 2);
+            const uint32_t acc = tmem_u + h * TN;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < TK / 8; ++ks) {
+                const uint64_t adv = static_cast<uint64_t>(2 * ks);  // +32 bytes per k-step inside the 128-byte swizzle row
+                mma_tf32_ts(acc, a_hi + 8 * ks, b_hi + adv, idesc, kb > 0 || ks > 0);
+                mma_tf32_ts(acc, a_hi + 8 * ks, b_lo + adv, idesc, true);
+                mma_tf32_ts(acc, a_lo + 8 * ks, b_hi + adv, idesc, true);
+              }
+              mma_commit(&empty_b[qb]);
+              if (h == H - 1) {
+                mma_commit(&empty_a[sa]);
+                if (kb == num_kb - 1) mma_commit(done_bar);
+              }
             }
-            mma_commit(&empty_a[sa]);
-            mma_commit(&empty_b[sb]);
-            if (kb == num_kb - 1) mma_commit(done_bar);
+            __syncwarp();
+            if (++qb == NB) { qb = 0; pb ^= 1; }
           }
-          __syncwarp();
         }
       }
-    } else if (warp == TC_THREADS / 32 + 1 && lane == 0) {  // ---- weight loader: one 32 KB bulk copy per k-block
-      int it = 0;
+    } else if (warp == TC_THREADS / 32 + 1 && lane == 0) {  // ---- weight loader: two 16 KB bulk copies (hi, lo) per slot
+      // image tile = g.b_tile_rows (128 or 256) weight rows x 32 k: [hi rows x 128 B | lo rows x 128 B]; the 128-row
+      // half `hh` of a 256-row tile is a contiguous 16 KB piece of each
+      const int R = g.b_tile_rows, per = R / TN;
+      const size_t stage_f = static_cast<size_t>(2) * R * TK;  // floats per image k-block
+      int qb = 0, pb = 0;
       for (int ti = 0;; ++ti) {
         mbar_wait_guarded(tile_bar, ti & 1);
         const int tile = ticket[ti & 7];
         if (tile >= ntiles) break;
         const int n_tile = tile % ntn;
-        const float *b_src = g.b_img + (static_cast<size_t>(n_tile) * g.b_img_kblocks) * (BST / 4);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % NB;
-          if (it >= NB) mbar_wait_guarded(&empty_b[s], ((it / NB) - 1) & 1);  // the MMAs that read this stage are done
-          if (kb == 0) tile_stamp(ti, 7);
-          mbar_expect_tx(&full_b[s], BST);
-          constexpr int PIECE = 16384;  // several bulk copies in flight per stage instead of one 32 / 64 KB copy
+        for (int kb = 0; kb < num_kb; ++kb) {
 #pragma unroll
-          for (int q = 0; q < BST / PIECE; ++q)
-            bulk_g2s(ring_b + s * BST + q * PIECE, b_src + static_cast<size_t>(kb) * (BST / 4) + q * (PIECE / 4), PIECE, &full_b[s]);
+          for (int h = 0; h < H; ++h) {
+            const int n128 = n_tile * H + h, T = n128 / per, hh = n128 - T * per;
+            const float *src = g.b_img + (static_cast<size_t>(T) * g.b_img_kblocks + kb) * stage_f + static_cast<size_t>(hh) * TN * TK;
+            mbar_wait_guarded(&empty_b[qb], pb ^ 1);  // the MMAs that read this slot are done (first use: passes)
+            if (kb == 0 && h == 0) tile_stamp(ti, 7);
+            mbar_expect_tx(&full_b[qb], BSL);
+            bulk_g2s(ring_b + qb * BSL, src, BSL / 2, &full_b[qb]);
+            bulk_g2s(ring_b + qb * BSL + BSL / 2, src + static_cast<size_t>(R) * TK, BSL / 2, &full_b[qb]);
+            if (++qb == NB) { qb = 0; pb ^= 1; }
+          }
         }
       }
     }
@@ -990,11 +1008,20 @@ int launch_tc_async_w(const GemmArgs &g, cudaStream_t stream) {
   return check_launch("gemm_tc_async_kernel");
 }
 
-// 128 x 256 tiles when the weight image was built with 256-row tiles and the output width is a multiple of 256
+// 128 x 256 tiles when the weight image was built with 256-row tiles and the cost model favours them: a wide tile stages
+// A once for 256 columns (0.8 us per k-block, MMA bound, against 2 x 0.6 us) but drains two accumulator halves, so with
+// few tiles (the deep levels: 4 ... 64 row tiles) twice as many narrow tiles on twice as many SMs finish earlier.
+// Per-tile constants from profiles/r2_tile_trace.txt.
 template <int AKIND, int EPI>
 int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
-  if (g.b_tile_rows == 256 && (g.N % 256) == 0) return launch_tc_async_w<AKIND, EPI, 256>(g, stream);
-  if (g.b_tile_rows != 128) return PN2_TC_UNSUPPORTED;
+  if (g.b_tile_rows != 128 && g.b_tile_rows != 256) return PN2_TC_UNSUPPORTED;
+  if (g.b_tile_rows == 256 && (g.N % 256) == 0) {
+    const int sms = sm_count() - persistent_spare() > 1 ? sm_count() - persistent_spare() : 1;
+    const int wide = ((g.M + TM - 1) / TM) * (g.N / 256), kb = (g.K + TK - 1) / TK;
+    const float cost_w = static_cast<float>((wide + sms - 1) / sms) * (0.8f * kb + 5.0f);
+    const float cost_n = static_cast<float>((2 * wide + sms - 1) / sms) * (0.6f * kb + 3.3f);
+    if (cost_w <= cost_n) return launch_tc_async_w<AKIND, EPI, 256>(g, stream);
+  }
   return launch_tc_async_w<AKIND, EPI, 128>(g, stream);
 }
 
