@@ -253,12 +253,32 @@ def _slot(param):
     return None if s is None else s.view(s.shape)
 
 
+# The weight gradient of a layer and its data gradient both start from dY and do not depend on each other.  On the deep
+# levels either GEMM is a few dozen tiles whose time is launch + prologue + tail, and on the shallow ones the tail of one
+# fills behind the other, so the weight gradients run on a second stream (forked / joined inside CUDA-graph capture like
+# the geometry stream) underneath the data-gradient chain.  Measured per step: never 2.521 ms, <= 8192 positions 2.466,
+# always 2.433 (profiles/r2_bench_wgrad_stream_*.json).  PN2_WGRAD_STREAM_ROWS: largest position count that forks.
+_WGRAD_STREAM_ROWS = int(os.environ.get("PN2_WGRAD_STREAM_ROWS", str(1 << 30)))
+_wgrad_streams = {}
+
+
+def _wgrad_stream(device):
+    s = _wgrad_streams.get(device.index)
+    if s is None:
+        s = _wgrad_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
 def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
     """Backward through the stack.  gz: position-major grad of the pooled output [groups, np_last]
     (overwritten).  first_dgrad(dy, L0) handles the input gradient of layer 0.  Returns the parameter
     gradients [(dW, dgamma, dbeta)] in layer order."""
     last = state[-1]
     groups = nrows // group
+    dev = last.y.device
+    main = torch.cuda.current_stream(dev)
+    side = _wgrad_stream(dev) if 0 < nrows <= _WGRAD_STREAM_ROWS else None
+    keep = []  # what the side stream reads stays referenced until the join (its blocks belong to the main stream's pool)
     stats, tiles = K.pool_bwd_prep(gz, out_pm, arg, last.y, groups, group, last.cout, last.np)
     ca, cb, cc, dgamma, dbeta = _bn_backward(last, stats, tiles)
     dy = K.rows_dy(last.y, gz, nrows, last.np, last.np, ca, cb, cc, arg=arg, group=group)
@@ -270,7 +290,16 @@ def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
             a_src = K.rows_bnrelu(P.y, nrows, P.np, P.np, P.scale, P.shift)
         else:
             a_src = rows0
-        dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device, out=_slot(L.params[0]))
+        if side is not None:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device, out=_slot(L.params[0]))
+            dw.record_stream(main)
+            keep.append((dy, a_src))
+        else:
+            dw = K.mlp_wgrad(dy, a_src, L.cout, L.cin, L.xyz_first, L.feat_pad, L.y.device, out=_slot(L.params[0]))
         grads[li] = (dw.view(L.cout, L.cin, 1, 1), dgamma, dbeta)
         if li > 0:
             dz, stats, tiles = K.mlp_dgrad_mask(dy, P.np, L.wp, P.y, P.scale, P.shift, wt=L.wt)
@@ -278,6 +307,9 @@ def _mlp_backward(state, rows0, nrows, gz, out_pm, arg, group, first_dgrad):
             dy = K.rows_dy(P.y, dz, nrows, P.np, P.np, ca, cb, cc)
         else:
             first_dgrad(dy, L)
+    if side is not None:
+        main.wait_stream(side)
+    del keep
     return grads
 
 
