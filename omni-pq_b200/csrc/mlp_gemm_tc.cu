@@ -180,6 +180,11 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const GemmArgs &g, int m0, 
   }
 }
 
+// Measured per 128 x 128 half (round 2, stamps inside this function, profiles/r2_epilogue_trace.txt): tensor-memory load
+// 0.1 us, shared-memory transpose 0.2-0.4, the store loop 1.1-1.3, shuffles + barrier + statistics 0.4-0.8.  The store
+// loop is the SM's write path -- 64 KB at ~32 B/clk -- not the chip's: starting the CTAs of a launch in four phases so that
+// their epilogues do not coincide changed nothing (93.2 vs 89.4 us on 131072 x 128 -> 256).  Hiding it needs stores that
+// drain under the NEXT tile's main loop (bulk stores from a staging buffer that does not alias the weight ring).
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, unsigned char *tiles,
                                             float (&red)[2][TC_THREADS / 32][32], int m0, int n0, int m_tile, int split,
@@ -723,11 +728,6 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   trace_stamp(g, blockIdx.x, 0, smid());
   trace_stamp(g, blockIdx.x, 1, globaltimer_ns());
 
-  auto draw = [&]() {  // thread 0
-    const int k = atomicAdd(g.tile_counter, 1);
-    if (k == ntiles - 1) *g.tile_counter = 0;
-    return 5 * grid_n + k;
-  };
   if (tid == 0) {
     for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], TC_THREADS); mbar_init(&raw_empty[s], TC_THREADS / 32); }
@@ -954,9 +954,12 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
       if (tid == 0) {
         tile_stamp(ti, 2);
         // draw the ticket five tiles ahead -- here, where this thread would otherwise only wait for the accumulator (the
-        // atomic's ~1 us round trip at the START of a tile delayed warp 0 and with it everybody); everybody reads it
-        // after the closing barrier below
-        ticket[(ti + 5) & 7] = draw();
+        // atomic's ~1 us round trip at the START of a tile delayed warp 0 and with it everybody, also when only its
+        // issue sits there and the result is first read here: 60.5 vs 55.6 us on 131072 x 128 -> 128); everybody reads
+        // it after the closing barrier below
+        const int k = atomicAdd(g.tile_counter, 1);
+        if (k == ntiles - 1) *g.tile_counter = 0;  // the last draw of the launch: nobody draws again
+        ticket[(ti + 5) & 7] = 5 * grid_n + k;
       }
       float4 yv[8];
       tc_epilogue_prefetch<EPI>(g, m0, n0, yv);

@@ -38,13 +38,6 @@ def run(fn, label):
         start = (x[:, 0] - t0) / 1e3
         row = "  ".join(f"{NAMES[k]} {rel[:, k].mean():6.2f}" for k in (1, 2, 3, 4, 5, 6, 7))
         print(f"  tile #{ti} ({int(sel.sum())} CTAs, starts at {start.mean():6.2f} us): {row}")
-    sel = t[:, 7, 0] > 0
-    if sel.sum() > 0:  # one k-block (tile 1, k-block 2) of warp 0: ns between the steps
-        x = t[sel, 7]
-        d = (x[:, 1:] - x[:, :-1]).mean(0)
-        steps = ["top-up issue", "raw_full wait", "lds + raw_empty arrive", "transform+split", "empty_a wait", "sttm + wait::st",
-                 "fence + full_a arrive"]
-        print("  one k-block of warp 0 (ns): " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(steps, d)) + f"  | total {float((x[:, 7] - x[:, 0]).mean()):6.0f}")
 
 
 def main():
