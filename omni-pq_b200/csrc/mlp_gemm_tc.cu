@@ -13,8 +13,12 @@
 //     B = the layer's weights): persistent, one CTA per SM, 16 producer warps + a converged MMA warp + a weight-loader
 //     warp; activations travel  global --cp.async--> raw ring in shared memory --transform, split--> TENSOR MEMORY
 //     (tcgen05.st), weights as a pre-split image by cp.async.bulk; MMAs in TS form (A from tensor memory).
-//   * gemm_tc_kernel<.., TRANS = true, ..>  -- weight-gradient GEMMs (K = positions): both operands are row sources,
-//     staged MN-major through registers by 16 producer warps, one CTA per (tile, position slice).
+//   * wgrad_tc_async_kernel -- weight-gradient GEMMs (K = positions): both operands are row sources; raw ring by
+//     cp.async, transposed on the way out of it with thread = channel (dY -> tensor memory, activation -> a K-major
+//     shared-memory tile), one CTA per (tile, position slice).
+// Both are bounded by INSTRUCTION ISSUE in the 16 producer warps (a k-block is ~250-350 instructions per warp, 4 issue
+// slots per SM and cycle), which is why their loops avoid cvt.rna.tf32 (expanded to ~7 instructions by ptxas),
+// generic-address loads and guarded spin loops on the hot path.
 // Both share the epilogue (tcgen05.ld -> per-warp shared-memory transpose -> row-contiguous 128-bit stores, BatchNorm
 // partial column sums, ReLU-mask / scatter-add variants).
 #include <atomic>
@@ -30,14 +34,8 @@ using namespace sm100;
 constexpr int TM = 128, TN = 128, TK = 32;          // CTA tile; TK fp32 = one 128-byte swizzle row
 constexpr int TC_THREADS = 512;                    // 16 producer / epilogue warps
 constexpr int TC_CTA_THREADS = TC_THREADS + 32;    // + one warp whose lane 0 only issues the MMAs
-constexpr int TC_ROWS_PER_THREAD = TM * 8 / TC_THREADS;  // 16-byte chunks of an operand k-block per thread (2)
-constexpr int TC_STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;             // 16 KB per operand half
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_KMAX = 1152;                        // largest K of the non-transposed form (coefficient staging)
-constexpr int TC_COEF_FLOATS = 3 * TC_KMAX + 2 * 128; // A: up to 3 vectors over K (or over 128 tile channels); B: 2 x 128
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers, scratch*/ + TC_COEF_FLOATS * 4;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr int TC_KMAX = 1152;                        // largest K of the forward / data-gradient form
 
 enum { TC_EPI_STORE = 0, TC_EPI_STORE_STATS = 1, TC_EPI_DGRAD_MASK = 2, TC_EPI_SCATTER = 3 };
 
@@ -50,46 +48,6 @@ struct Raw {
   float4 d;   // DY: dz; DYPOOL: pooled gz
   uchar4 a;   // DYPOOL: arg-max slot
 };
-
-template <int KIND>
-__device__ __forceinline__ Raw fetch_raw(const pn2_rows &s, const RowCtx &c, int c4) {
-  Raw r;
-  r.x = zero4(); r.d = zero4(); r.a = make_uchar4(0, 0, 0, 0);
-  if (!c.valid || c4 >= s.cols) return r;
-  if (KIND == PN2_ROWS_GATHER) {
-    if (c4 < s.feat_cols) r.x = ldg4(s.x + c.off + c4);
-    return r;
-  }
-  r.x = ldg4(s.x + c.off + c4);
-  if (KIND == PN2_ROWS_DY) r.d = ldg4(s.dz + c.off + c4);
-  if (KIND == PN2_ROWS_DYPOOL) {
-    r.d = ldg4(s.dz + c.goff + c4);
-    r.a = __ldg(reinterpret_cast<const uchar4 *>(s.arg + c.goff + c4));
-  }
-  return r;
-}
-
-// coef: shared-memory copies of the source's per-channel vectors c0,c1,c2, indexed by (c4 - coef_base)
-template <int KIND>
-__device__ __forceinline__ float4 apply_raw(const pn2_rows &s, const RowCtx &c, int c4, const Raw &r,
-                                            const float *coef, int coef_ld, int coef_base) {
-  if (!c.valid || c4 >= s.cols) return zero4();
-  if (KIND == PN2_ROWS_PLAIN) return r.x;
-  if (KIND == PN2_ROWS_GATHER) return c4 < s.feat_cols ? r.x : make_float4(c.gx, c.gy, c.gz, 0.f);
-  const int ci = c4 - coef_base;
-  const float4 k0 = *reinterpret_cast<const float4 *>(coef + ci);
-  const float4 k1 = *reinterpret_cast<const float4 *>(coef + coef_ld + ci);
-  if (KIND == PN2_ROWS_BNRELU)
-    return make_float4(relu_nan(fmaf(r.x.x, k0.x, k1.x)), relu_nan(fmaf(r.x.y, k0.y, k1.y)),
-                       relu_nan(fmaf(r.x.z, k0.z, k1.z)), relu_nan(fmaf(r.x.w, k0.w, k1.w)));
-  const float4 k2 = *reinterpret_cast<const float4 *>(coef + 2 * coef_ld + ci);
-  float4 dz = r.d;
-  if (KIND == PN2_ROWS_DYPOOL)
-    dz = make_float4(r.a.x == c.slot ? dz.x : 0.f, r.a.y == c.slot ? dz.y : 0.f, r.a.z == c.slot ? dz.z : 0.f,
-                     r.a.w == c.slot ? dz.w : 0.f);
-  return make_float4(fmaf(k2.x, r.x.x, fmaf(k0.x, dz.x, k1.x)), fmaf(k2.y, r.x.y, fmaf(k0.y, dz.y, k1.y)),
-                     fmaf(k2.z, r.x.z, fmaf(k0.z, dz.z, k1.z)), fmaf(k2.w, r.x.w, fmaf(k0.w, dz.w, k1.w)));
-}
 
 template <int KIND>
 __device__ __forceinline__ void stage_coef(const pn2_rows &s, float *coef, int coef_ld, int base, int count, int tid,
@@ -286,225 +244,6 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, 
     }
   }
 
-}
-
-// TRANS = false: A rows are tile rows (positions), B rows are output channels, both K-contiguous in memory.
-// TRANS = true (weight gradient): K runs over POSITIONS; A = dY source and B = activation source are both
-// position rows with channels contiguous.  They are transposed while they are staged into the same K-major
-// tiles: a lane holds 4 channels of one position and writes them with four 4-byte stores whose order is
-// rotated per lane, so that the 32 lanes of a store (8 channel quads x 4 consecutive positions) hit 32
-// different banks.  blockIdx.z selects a slice of positions and the partial tile goes to
-// out + blockIdx.z * out_split_stride.
-// Global access pattern (both forms): 8 consecutive lanes cover one 128-byte row segment, a warp-wide
-// 128-bit access touches 4 lines instead of 32.
-template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
-__global__ void __launch_bounds__(TC_CTA_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
-  pdl_prologue();
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(tiles + TC_STAGES * STAGE_BYTES);  // [TC_STAGES] MMAs of the stage done
-  uint64_t *full_bar = empty_bar + TC_STAGES;                                           // [TC_STAGES] stage written (16 warps)
-  uint64_t *done_bar = full_bar + TC_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
-  float *coef_a = reinterpret_cast<float *>(tiles + TC_STAGES * STAGE_BYTES + 256);  // [3][coef_ld_a]
-  float *coef_b = coef_a + 3 * TC_KMAX;                                              // [2][128]
-  __shared__ float red[2][TC_THREADS / 32][32];  // per-warp column partials for the statistics epilogues
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
-  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  trace_stamp(g, cta_id, 0, smid());
-  trace_stamp(g, cta_id, 1, globaltimer_ns());
-
-  if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&full_bar[s], TC_THREADS / 32);
-    }
-    mbar_init(done_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
-  const bool producer = warp < TC_THREADS / 32;  // warp 16: lane 0 issues the MMAs, nothing else
-
-  const uint32_t idesc = idesc_tf32(TM, TN, TRANS);
-  const int k_begin = TRANS ? blockIdx.z * g.k_per_split : 0;
-  const int k_end = TRANS ? min(g.K, k_begin + g.k_per_split) : g.K;
-  const int num_kb = k_end > k_begin ? (k_end - k_begin + TK - 1) / TK : 0;
-
-  const int coef_ld_a = TRANS ? 128 : TC_KMAX;
-  const int coef_base_a = TRANS ? m0 : 0, coef_base_b = TRANS ? n0 : 0;
-
-  // ---- producer mapping --------------------------------------------------------------------------------
-  // plain form : chunk = tid % 8 (16 bytes of the 128-byte k-row), rows rsub + 64*i (i < 2) of the A / B tile
-  // transposed : lane = 16-byte channel quad of the tile's 128 channels (a warp reads one position's 512
-  //              contiguous bytes), positions warp + 16*i (i < 2) of the k-block, stored MN-major:
-  //              offset(k, q) = (q/8)*4096 + (k/4)*512 + (k%4)*128 + (((q%8)/2 ^ k%4) * 32) + (q%2)*16
-  constexpr int R = TC_ROWS_PER_THREAD;
-  const int chunk = tid & 7, rsub = tid >> 3;
-  uint32_t off[R];
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    if (!TRANS) {
-      off[i] = sw128_offset(rsub + 64 * i, chunk);
-    } else {
-      const int k = warp + 16 * i;
-      off[i] = static_cast<uint32_t>((lane >> 3) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((lane & 7) >> 1) ^ (k & 3)) << 5) +
-                                     (lane & 1) * 16);
-    }
-  }
-
-  RowCtx ca[R], cb[R];
-  auto make_ctx = [&](int kb, RowCtx *xa, RowCtx *xb) {  // transposed form: this thread's positions in k-block kb
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const int p = k_begin + kb * TK + warp + 16 * i;
-      const int r = (kb < num_kb && p < k_end) ? p : 0x7fffffff;
-      xa[i] = row_ctx<AKIND>(g.A, r);
-      xb[i] = row_ctx<BKIND>(g.B, r);
-    }
-  };
-  RowCtx na[R], nb[R];  // transposed form: contexts of the NEXT k-block, resolved one block ahead of its loads so
-                        // that a gather's index load and the row loads that depend on it sit in different iterations
-  auto col_a = [&](int kb) { return TRANS ? m0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
-  auto col_b = [&](int kb) { return TRANS ? n0 + lane * 4 : k_begin + kb * TK + chunk * 4; };
-  Raw da[2][R], db[2][R];  // two prefetch register sets, addressed with compile-time indices (loop unrolled by 2)
-  if (producer) {
-    if (TRANS) {
-      make_ctx(0, ca, cb);
-      make_ctx(1, na, nb);
-    } else {
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        ca[i] = row_ctx<AKIND>(g.A, m0 + rsub + 64 * i);
-        cb[i] = row_ctx<BKIND>(g.B, n0 + rsub + 64 * i);
-      }
-    }
-    if (num_kb > 0) {
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        da[0][i] = fetch_raw<AKIND>(g.A, ca[i], col_a(0));
-        db[0][i] = fetch_raw<BKIND>(g.B, cb[i], col_b(0));
-      }
-    }
-    // per-channel coefficient vectors of the sources -> shared memory (channels = k for the plain form, the
-    // tile's 128 output rows / columns for the transposed form); staged while the first k-block's loads fly
-    stage_coef<AKIND>(g.A, coef_a, coef_ld_a, coef_base_a, TRANS ? 128 : min(g.K, TC_KMAX), tid);
-    if (TRANS) stage_coef<BKIND>(g.B, coef_b, 128, coef_base_b, 128, tid);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
-  trace_stamp(g, cta_id, 2, globaltimer_ns());
-
-  // ---- MMA issue (lane 0 of warp 16, which does nothing else): wait until all 16 producer warps have written
-  // the stage, issue its 12 MMAs and commit them to the stage's "empty" barrier.  No block barrier, and the
-  // issuing thread is not a producer: a thread that stages operands and issues MMAs holds its warp back
-  // (a __syncthreads per k-block serialised staging and MMA issue: 1.3-1.9 us per k-block against 0.4 us of MMA
-  // time, profiles/c3_gemm_trace.txt).
-  if (!producer) {
-    // MMA warp, CONVERGED: all 32 lanes run the loop on warp-uniform values and the MMAs / commits are issued under
-    // elect.sync, so the descriptors live in uniform registers (see elect_one() in pn2_sm100.cuh)
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % TC_STAGES;
-      mbar_wait_guarded(&full_bar[s], (kb / TC_STAGES) & 1);
-      tc_fence_after_sync();
-      const uint32_t base = smem_addr(tiles + s * STAGE_BYTES);
-      uint64_t a_hi, a_lo, b_hi, b_lo, step;
-      if (TRANS) {
-        a_hi = smem_desc_mn_sw128_32b(base, 4096, 512); a_lo = smem_desc_mn_sw128_32b(base + TILE_BYTES, 4096, 512);
-        b_hi = smem_desc_mn_sw128_32b(base + 2 * TILE_BYTES, 4096, 512);
-        b_lo = smem_desc_mn_sw128_32b(base + 3 * TILE_BYTES, 4096, 512);
-        step = 1024 >> 4;  // 8 k-rows per MMA = two groups of 4 rows
-      } else {
-        a_hi = smem_desc_sw128(base); a_lo = smem_desc_sw128(base + TILE_BYTES);
-        b_hi = smem_desc_sw128(base + 2 * TILE_BYTES); b_lo = smem_desc_sw128(base + 3 * TILE_BYTES);
-        step = 32 >> 4;    // +32 bytes per k-step inside the 128-byte swizzle row
-      }
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint64_t adv = step * ks;
-          mma_tf32(tmem_u, a_hi + adv, b_hi + adv, idesc, kb > 0 || ks > 0);
-          mma_tf32(tmem_u, a_hi + adv, b_lo + adv, idesc, true);
-          mma_tf32(tmem_u, a_lo + adv, b_hi + adv, idesc, true);
-        }
-        mma_commit(&empty_bar[s]);
-        if (kb == num_kb - 1) mma_commit(done_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ---- producers: no block-wide barrier inside the loop; a stage is handed over with one mbarrier arrival
-    // per warp and reclaimed when the MMAs that read it have completed
-    // ROT = false: the two prefetch register sets are addressed with compile-time indices (loop unrolled by 2);
-    // ROT = true (what launch_tc instantiates): one loop body, the sets are rotated with register copies (fewer live
-    // registers; the copy waits for the load it has just issued).
-    constexpr int NU = ROT ? 1 : 2;
-    for (int kb0 = 0; kb0 < num_kb; kb0 += NU) {
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int kb = kb0 + u;
-        if (kb >= num_kb) break;
-        const int s = kb % TC_STAGES;
-        // 1. put the next k-block's loads in flight (into the other register set: no copies, a move out of a
-        //    register with a load in flight would stall until the data is back)
-        if (kb + 1 < num_kb) {
-#pragma unroll
-          for (int i = 0; i < R; ++i) {
-            da[u ^ 1][i] = fetch_raw<AKIND>(g.A, TRANS ? na[i] : ca[i], col_a(kb + 1));
-            db[u ^ 1][i] = fetch_raw<BKIND>(g.B, TRANS ? nb[i] : cb[i], col_b(kb + 1));
-          }
-        }
-        // 2. the stage is free once the MMAs that read it (block kb - STAGES) have completed
-        if (kb >= TC_STAGES) mbar_wait_guarded(&empty_bar[s], ((kb / TC_STAGES) - 1) & 1);
-        unsigned char *st = tiles + s * STAGE_BYTES;
-        // 3. transform + split + store the current block (128-bit stores, conflict-free in both layouts)
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const float4 va = apply_raw<AKIND>(g.A, ca[i], col_a(kb), da[u][i], coef_a, coef_ld_a, coef_base_a);
-          const float4 vb = apply_raw<BKIND>(g.B, cb[i], col_b(kb), db[u][i], coef_b, 128, coef_base_b);
-          float4 hi, lo;
-          split_tf32(va.x, hi.x, lo.x); split_tf32(va.y, hi.y, lo.y);
-          split_tf32(va.z, hi.z, lo.z); split_tf32(va.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + 0 * TILE_BYTES + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + 1 * TILE_BYTES + off[i]) = lo;
-          split_tf32(vb.x, hi.x, lo.x); split_tf32(vb.y, hi.y, lo.y);
-          split_tf32(vb.z, hi.z, lo.z); split_tf32(vb.w, hi.w, lo.w);
-          *reinterpret_cast<float4 *>(st + 2 * TILE_BYTES + off[i]) = hi;
-          *reinterpret_cast<float4 *>(st + 3 * TILE_BYTES + off[i]) = lo;
-        }
-        fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-        // 4. contexts are computed values (cheap to move); resolve the block after the next one
-        if (TRANS) {
-#pragma unroll
-          for (int i = 0; i < R; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
-          make_ctx(kb + 2, na, nb);
-        }
-        if (ROT) {
-#pragma unroll
-          for (int i = 0; i < R; ++i) { da[0][i] = da[1][i]; db[0][i] = db[1][i]; }
-        }
-      }
-    }
-    float4 yv[8];
-    tc_epilogue_prefetch<EPI>(g, m0, n0, yv);
-    if (num_kb > 0) mbar_wait_guarded(done_bar, 0);
-    tc_fence_after_sync();
-    trace_stamp(g, cta_id, 3, globaltimer_ns());
-    tc_epilogue<EPI>(g, tmem_d, tiles, red, m0, n0, blockIdx.x, blockIdx.z, num_kb > 0, yv);
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
-  trace_stamp(g, cta_id, 4, globaltimer_ns());
-  trace_stamp(g, cta_id, 5, static_cast<unsigned long long>(num_kb));
 }
 
 // ---- forward / data-gradient kernels with a bulk-copied weight operand ---------------------------------------
@@ -744,7 +483,7 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(TM, TN, false);
+  const uint32_t idesc = idesc_tf32(TM, TN);
   trace_stamp(g, blockIdx.x, 2, globaltimer_ns());
 
   if (!producer) {
@@ -1124,7 +863,7 @@ wgrad_tc_async_kernel(const __grid_constant__ GemmArgs g) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = fold ? idesc_tf32(TM, TN + 16, false) : idesc_tf32(TM, TN, false);
+  const uint32_t idesc = fold ? idesc_tf32(TM, TN + 16) : idesc_tf32(TM, TN);
   trace_stamp(g, cta_id, 2, globaltimer_ns());
 
   if (!producer) {  // ---- MMA warp, converged
@@ -1375,30 +1114,6 @@ int launch_wgrad_async(const GemmArgs &g, int splits, cudaStream_t stream) {
   return check_launch("wgrad_tc_async_kernel");
 }
 
-template <int AKIND, int BKIND, bool TRANS, int EPI, bool ROT>
-int launch_tc_rot(const GemmArgs &g, int splits, cudaStream_t stream) {
-  auto kernel = gemm_tc_kernel<AKIND, BKIND, TRANS, EPI, ROT>;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (configured_dev != dev) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    configured_dev = dev;
-  }
-  dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, splits);
-  GemmArgs a = g;
-  gemm_trace_target(&a.trace, &a.trace_cap);
-  pn2::launch(kernel, dim3(grid), dim3(TC_CTA_THREADS), TC_SMEM, stream, a);
-  return check_launch("gemm_tc_kernel");
-}
-
-template <int AKIND, int BKIND, bool TRANS, int EPI>
-int launch_tc(const GemmArgs &g, int splits, cudaStream_t stream) {
-  // prefetch register sets rotated with copies (ROT = true): the statically indexed variant spills under the 96-register
-  // cap of a 17-warp CTA for the DYPOOL / GATHER sources (wgrad 1.31 vs 1.09 ms per step, profiles/r1_c8_*)
-  return launch_tc_rot<AKIND, BKIND, TRANS, EPI, true>(g, splits, stream);
-}
-
 }  // namespace
 
 // development aid: per-CTA phase timestamps of the next tensor-core GEMM launches (tools/gemm_trace.py)
@@ -1413,8 +1128,7 @@ void gemm_trace_target(unsigned long long **buf, int *cap) {
 bool wgrad_fold_ok(const void *gemm_args) {
   static const bool on = [] {
     const char *e = getenv("PN2_WGRAD_FOLD");
-    const char *a = getenv("PN2_WGRAD_ASYNC");
-    return (e == nullptr || e[0] != '0') && (a == nullptr || a[0] != '0');
+    return e == nullptr || e[0] != '0';
   }();
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   return on && gemm_tc_enabled() && g.A.kind == PN2_ROWS_DY && g.B.kind == PN2_ROWS_GATHER && g.B.use_xyz && g.B.feat_cols >= TN &&
@@ -1465,13 +1179,8 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
 int gemm_tc_wgrad_launch(const void *gemm_args, int splits, cudaStream_t stream) {
   const GemmArgs &g = *static_cast<const GemmArgs *>(gemm_args);
   if (!gemm_tc_enabled()) return PN2_TC_UNSUPPORTED;
-  static const bool async_on = [] {  // PN2_WGRAD_ASYNC=0: the register-staged MN-major kernel (A/B comparisons)
-    const char *e = getenv("PN2_WGRAD_ASYNC");
-    return e == nullptr || e[0] != '0';
-  }();
-#define PN2_TC_W(AK, BK)                                                \
-  if (g.A.kind == AK && g.B.kind == BK)                                 \
-    return async_on ? launch_wgrad_async<AK, BK>(g, splits, stream) : launch_tc<AK, BK, true, TC_EPI_STORE>(g, splits, stream);
+#define PN2_TC_W(AK, BK) \
+  if (g.A.kind == AK && g.B.kind == BK) return launch_wgrad_async<AK, BK>(g, splits, stream);
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_PLAIN)
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_BNRELU)
   PN2_TC_W(PN2_ROWS_DY, PN2_ROWS_GATHER)

@@ -92,35 +92,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) {
   return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
 }
 
-// MN-major operand tile [k rows][128 contiguous MN elements], 128-byte swizzle: atoms of 32 MN elements
-// (128 B) x 8 k-rows = 1024 B; consecutive k-groups of an atom column are SBO = 1024 B apart, atom columns
-// LBO bytes apart (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// 32-bit elements in MN-major use the "128B swizzle, 32-byte base" layout (CUTLASS Layout_MN_SW128_32B_Atom:
-// Swizzle<2,5,2> over 128 B x 4 k-rows): the 32-byte chunk index inside a 128-byte row is XORed with
-// (k-row % 4); groups of 4 k-rows are SBO bytes apart, columns of 32 MN elements LBO bytes apart.
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(1) << 61;  // SWIZZLE_128B_BASE32B
-  return d;
-}
-
-// kind::tf32, fp32 accumulate, M x N tile; mn_major selects MN-major (transposed) A and B operands
-__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, bool mn_major = false) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// kind::tf32, fp32 accumulate, M x N tile, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread

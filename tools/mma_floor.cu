@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(288, 1) floor_kernel(int iters, int noise_warp
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
-  const uint32_t idesc = idesc_tf32(128, N, false);
+  const uint32_t idesc = idesc_tf32(128, N);
   if (warp == 8 && lane == 0) {
     const uint64_t ah = smem_desc_sw128(smem_addr(a_hi)), al = smem_desc_sw128(smem_addr(a_lo));
     const uint64_t bh = smem_desc_sw128(smem_addr(b_hi)), bl = smem_desc_sw128(smem_addr(b_lo));

@@ -33,12 +33,6 @@ __device__ __forceinline__ void arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 __global__ void __launch_bounds__(576, 1) k(int iters, int feat, const float *bimg, unsigned long long *out) {
   extern __shared__ unsigned char raw[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -64,7 +58,7 @@ __global__ void __launch_bounds__(576, 1) k(int iters, int feat, const float *bi
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_slot, 0);
-  const uint32_t idesc = idesc_tf32(128, 128, false);
+  const uint32_t idesc = idesc_tf32(128, 128);
   if (warp == 16 && (feat & 32)) {  // converged MMA warp
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
