@@ -142,7 +142,10 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const GemmArgs &g, int m0, 
 // 0.1 us, shared-memory transpose 0.2-0.4, the store loop 1.1-1.3, shuffles + barrier + statistics 0.4-0.8.  The store
 // loop is the SM's write path -- 64 KB at ~32 B/clk -- not the chip's: starting the CTAs of a launch in four phases so that
 // their epilogues do not coincide changed nothing (93.2 vs 89.4 us on 131072 x 128 -> 256).  Hiding it needs stores that
-// drain under the NEXT tile's main loop (bulk stores from a staging buffer that does not alias the weight ring).
+// drain under the NEXT tile's main loop.  Tried: the tile staged row-major in the (idle) weight ring and written out by
+// the weight-loader warp with 512-byte cp.async.bulk shared -> global stores while the producers go on -- correct
+// (73 / 73 GPU tests) but much slower, 145 vs 85 us on 131072 x 128 -> 256: the bulk-store path drains a 64 KB block
+// more slowly than 16 warps of 128-bit stores, and the next tile's weights wait for it (they share the memory).
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs &g, uint32_t tmem_d, unsigned char *tiles,
                                             float (&red)[2][TC_THREADS / 32][32], int m0, int n0, int m_tile, int split,

@@ -2,10 +2,7 @@
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
-( timeout 300 python tools/gemm_bench.py fwd ) > $O/x_gemm.txt 2>&1
-( timeout 300 python tools/gemm_bench.py dgrad ) >> $O/x_gemm.txt 2>&1
-( PN2_TC_STAGGER=0 timeout 300 python tools/gemm_bench.py fwd ) > $O/x_gemm0.txt 2>&1
-( PN2_TC_STAGGER=0 timeout 300 python tools/gemm_bench.py dgrad ) >> $O/x_gemm0.txt 2>&1
+( timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_fused.py -m gpu -q -x --tb=short 2>&1 | tail -30 ) > $O/x_pytest.log
+( timeout 300 python tools/gemm_bench.py all ) > $O/x_gemm.txt 2>&1
 ( timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-ref-gpu ) > $O/x_bench.json 2> $O/x_bench.err
-( PN2_TC_STAGGER=0 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-ref-gpu ) > $O/x_bench_st0.json 2> $O/x_bench_st0.err
 echo done
