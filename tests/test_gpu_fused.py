@@ -197,6 +197,32 @@ def test_sa_three_layer_xyz_grad_matches_oracle(K, O):
     _check_module_grads(ours, oracle)
 
 
+@pytest.mark.parametrize("mlp,nsample", [([128, 48], 5), ([128, 40, 24], 5), ([256, 32, 16], 16), ([128, 36], 64)])
+def test_sa_weight_gradient_xyz_block_layouts(mlp, nsample, K, O):
+    """Weight gradient of the gathered first layer when the feature width is a multiple of 128, i.e. the 4-column xyz block
+    starts a new 128-column tile: one layer = pooled dY source, xyz block in an n-tile of its own; several layers = plain dY
+    source, xyz block folded into the last feature tile as MMA columns 128..143 (mlp_gemm_tc.cu, WgCfg::kFoldable).
+    Odd nsample / position counts that are no multiple of 32: partial k-blocks, pool slots that wrap inside a k-block."""
+    import pointnet2_modules as M
+    kw = dict(npoint=37, radius=0.35, nsample=nsample, use_xyz=True, normalize_xyz=True)
+    ours, oracle = _pair(lambda: M.PointnetSAModuleVotes(mlp=list(mlp), **kw), lambda: O.OracleSAModuleVotes(mlp=list(mlp), **kw),
+                         seed=13, randomise_bn=True)
+    ours.train()
+    oracle.train()
+    xyz, feats = O.uniform_cloud(2, 300, mlp[0], seed=21)
+    x_dev, x_cpu = xyz.cuda().requires_grad_(True), xyz.clone().requires_grad_(True)
+    f_dev, f_cpu = feats.cuda().requires_grad_(True), feats.clone().requires_grad_(True)
+    new_xyz, out, inds = ours(x_dev, f_dev)
+    new_xyz_o, out_o, inds_o = oracle(x_cpu, f_cpu)
+    assert torch.equal(inds.cpu(), inds_o) and rel(out, out_o) <= FEAT_TOL
+    cot = torch.randn(out_o.shape, generator=torch.Generator().manual_seed(5))
+    (out * cot.cuda()).sum().backward()
+    (out_o * cot).sum().backward()
+    assert rel(f_dev.grad, f_cpu.grad) <= GRAD_TOL
+    assert rel(x_dev.grad, x_cpu.grad) <= GRAD_TOL
+    _check_module_grads(ours, oracle)
+
+
 def test_sa_without_features_and_given_inds(K, O):
     import pointnet2_modules as M
     kw = dict(npoint=64, radius=0.25, nsample=8, use_xyz=True, normalize_xyz=False)

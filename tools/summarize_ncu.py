@@ -69,7 +69,7 @@ def main():
         per = collections.defaultdict(list)
         for r in rows:
             name = r["Kernel Name"]
-            key = ("gemm_tc_kernel" if "gemm_tc" in name else "gemm_kernel" if "gemm_kernel" in name else
+            key = ("gemm_tc_kernel" if ("gemm_tc" in name or "wgrad_tc" in name) else "gemm_kernel" if "gemm_kernel" in name else
                    "fps_kernel" if "fps_" in name else name.split("(")[0].split("::")[-1])
             per[key].append(r.get("dram__bytes_read.sum_bytes", 0) + r.get("dram__bytes_write.sum_bytes", 0))
         for k, v in per.items():
