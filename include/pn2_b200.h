@@ -141,7 +141,8 @@ typedef struct pn2_rows {
  * input channels (the xyz channels QueryAndGroup puts first) behind the `feat_pad` feature channels so
  * that gathered feature rows stay 16-byte aligned: k' = [features 0..cin-4 | pad | x y z 0].
  * Each buffer additionally carries, right after the plain matrix, the tensor-core image of that matrix
- * (every 128-row x 32-column block split into tf32 hi / lo halves, in the UMMA 128-byte-swizzle layout) which the
+ * (every 128-row x 32-column block -- 256-row blocks when the matrix has a multiple of 256 rows -- split into tf32
+ * hi / lo halves, in the UMMA 128-byte-swizzle layout; the kernels read either block size) which the
  * forward / dgrad kernels fetch with one bulk copy per k-block.  Sizes, in floats:
  * wt: pn2_mlp_weight_floats(kp, np), wp: pn2_mlp_weight_floats(np, kp). */
 long long pn2_mlp_weight_floats(int rows, int cols);
