@@ -1140,6 +1140,14 @@ bool wgrad_fold_ok(const void *gemm_args) {
          g.B.feat_cols % TN == 0 && g.B.cols == g.B.feat_cols + 4;
 }
 
+static bool small_k_ffma() {
+  static const bool on = [] {
+    const char *e = getenv("PN2_TC_SMALLK_FFMA");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 bool gemm_tc_wide_enabled() {
   static const bool on = [] {
     const char *e = getenv("PN2_TC_WIDE");
@@ -1164,6 +1172,9 @@ int gemm_tc_launch(int akind, int epi, const void *gemm_args, cudaStream_t strea
   if (!gemm_tc_enabled() || g.B.kind != PN2_ROWS_PLAIN || g.K > TC_KMAX) return PN2_TC_UNSUPPORTED;
   if (akind != PN2_ROWS_PLAIN && akind != PN2_ROWS_GATHER && g.K > 640) return PN2_TC_UNSUPPORTED;  // coefficient staging
   if (g.b_img == nullptr) return PN2_TC_UNSUPPORTED;  // the weight operand comes as the pre-split image only
+  // K <= 16 (the first layer of a level without input features: xyz only): one k-block per tile, i.e. a launch that is
+  // all tile start-up and epilogue; the FFMA kernel writes the same output at memory speed
+  if (g.K <= 16 && epi == TC_EPI_STORE_STATS && small_k_ffma()) return PN2_TC_UNSUPPORTED;
 #define PN2_TC_CASE(AK, EP) \
   if (akind == AK && epi == EP) return launch_tc_async<AK, EP>(g, stream);
   PN2_TC_CASE(PN2_ROWS_PLAIN, TC_EPI_STORE_STATS)
