@@ -61,6 +61,27 @@ def test_argument_errors_are_codes_not_exits(built_lib):
     assert lib.pn2_three_interpolate(2, 0, 4, 4, None, None, None, None, None) == 0
 
 
+def test_wgrad_workspace_covers_both_tilings(built_lib):
+    """pn2_mlp_wgrad_workspace is what a binder allocates BEFORE it knows the row sources, so it must cover the larger of
+    the two slice counts: the plain tiling and, for kp = 128 m + 4 (gathered source, xyz block folded into the last
+    feature tile -- one n-tile fewer, hence more position slices), the folded one.  Host arithmetic only."""
+    lib = ctypes.CDLL(built_lib)
+    lib.pn2_mlp_wgrad_workspace.restype = ctypes.c_longlong
+    sms = 148  # without a device the library assumes a B200
+    for rows, np_, kp in [(131072, 128, 8), (32768, 256, 260), (8192, 256, 516), (4096, 256, 516), (370, 48, 132), (1, 4, 4)]:
+        ws = lib.pn2_mlp_wgrad_workspace(rows, np_, kp)
+        assert ws > 0 and ws % (np_ * kp) == 0
+        slices = ws // (np_ * kp)
+        tiles_m, tiles_n = -(-np_ // 128), -(-kp // 128)
+        cap = max(1, -(-rows // 128))                    # a slice is at least 128 positions
+        plain = max(1, min(sms // (tiles_m * tiles_n), cap, 512))
+        assert slices >= plain
+        if kp > 128 and kp % 128 == 4:
+            folded = max(1, min(sms // (tiles_m * (tiles_n - 1)), cap, 512))
+            assert slices >= folded > 0
+        assert slices * tiles_m * max(tiles_n - 1, 1) <= max(sms, tiles_m * tiles_n)  # still one wave of CTAs
+
+
 def test_python_binding_rejects_cpu_tensors(built_lib):
     """Same contract as the reference wrappers: CPU tensors -> RuntimeError ("CPU not supported",
     sampling.cpp:41), wrong dtype / layout -> RuntimeError (utils.h:10-30).  There is no fallback."""
