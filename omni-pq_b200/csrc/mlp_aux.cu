@@ -437,6 +437,88 @@ fp_interpolate_kernel(int n, int m, int c4n, int ld_known, const float *__restri
   }
 }
 
+// The backbone's FP modules have 512 / 1024 unknown points: a thread per point is 16 / 32 CTAs of one busy warp each
+// (45 us per launch, on the critical path of the step).  Here a WARP owns a point: its lanes scan the known points
+// 32 apart, each keeping its three nearest in index order, and the warp then extracts three times the smallest
+// (distance, index) pair -- exactly the triple three_nn_kernel's sequential scan with strict `<` ends with (equal
+// distances keep the lower index; slots nobody fills stay (inf, 0)) -- and blends the three rows, lanes across channels.
+__global__ void __launch_bounds__(kFpThreads)
+fp_interpolate_warp_kernel(int n, int m, int c4n, int ld_known, const float *__restrict__ unknown,
+                           const float *__restrict__ known, const float *__restrict__ known_pm, float *__restrict__ out,
+                           int ldo, int *__restrict__ idx_out, float *__restrict__ w_out) {
+  pdl_prologue();
+  __shared__ float tile[kFpTile * 3];
+  const int b = blockIdx.y;
+  unknown += static_cast<size_t>(b) * n * 3;
+  known += static_cast<size_t>(b) * m * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * (kFpThreads / 32) + warp;
+  const bool live = j < n;
+  const int jj = live ? j : n - 1;
+  const float ux = unknown[jj * 3 + 0], uy = unknown[jj * 3 + 1], uz = unknown[jj * 3 + 2];
+  float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int base = 0; base < m; base += kFpTile) {
+    const int tn = min(kFpTile, m - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += kFpThreads) tile[i] = known[base * 3 + i];
+    __syncthreads();
+    for (int k = lane; k < tn; k += 32) {  // (stride of 3 floats between lanes: conflict-free)
+      const float d = dist2(ux, uy, uz, tile[k * 3 + 0], tile[k * 3 + 1], tile[k * 3 + 2]);
+      if (d < b3) {
+        const int kk = base + k;
+        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk; }
+        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = kk; }
+        else { b3 = d; i3 = kk; }
+      }
+    }
+  }
+  // distances are >= 0 (or never stored: NaN fails `<`), so their bit patterns order like the values and
+  // (distance bits << 32 | index) orders like (distance, index)
+  float rd[3];
+  int ri[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(b1)) << 32) | static_cast<unsigned>(i1);
+    unsigned long long best = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    rd[t] = __uint_as_float(static_cast<unsigned>(best >> 32));
+    ri[t] = static_cast<int>(best & 0xffffffffu);
+    if (key == best) { b1 = b2; i1 = i2; b2 = b3; i2 = i3; b3 = CUDART_INF_F; i3 = 0; }  // (only fillers can tie across lanes)
+  }
+  if (!live) return;
+  // dist = sqrt(dist2); recip = 1/(dist + 1e-8); w = recip / sum(recip)   (left-to-right sum like torch.sum)
+  const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(rd[0]), 1e-8f));
+  const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(rd[1]), 1e-8f));
+  const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(rd[2]), 1e-8f));
+  const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+  const float wa = __fdiv_rn(r1, norm), wb = __fdiv_rn(r2, norm), wc = __fdiv_rn(r3, norm);
+  if (lane == 0) {
+    int *io = idx_out + (static_cast<size_t>(b) * n + j) * 3;
+    float *wo = w_out + (static_cast<size_t>(b) * n + j) * 3;
+    io[0] = ri[0]; io[1] = ri[1]; io[2] = ri[2];
+    wo[0] = wa; wo[1] = wb; wo[2] = wc;
+  }
+  const float *kp = known_pm + static_cast<size_t>(b) * m * ld_known;
+  const float *ra = kp + static_cast<size_t>(ri[0]) * ld_known;
+  const float *rb = kp + static_cast<size_t>(ri[1]) * ld_known;
+  const float *rc = kp + static_cast<size_t>(ri[2]) * ld_known;
+  float *o = out + (static_cast<size_t>(b) * n + j) * ldo;
+  for (int q = lane; q < c4n; q += 32) {
+    const float4 a = ldg4(ra + q * 4), bb = ldg4(rb + q * 4), cc = ldg4(rc + q * 4);
+    float4 r;  // interpolate_gpu.cu:103-104 contraction: p2*w2, then fma p1*w1, then fma p3*w3
+    r.x = __fmaf_rn(cc.x, wc, __fmaf_rn(a.x, wa, __fmul_rn(bb.x, wb)));
+    r.y = __fmaf_rn(cc.y, wc, __fmaf_rn(a.y, wa, __fmul_rn(bb.y, wb)));
+    r.z = __fmaf_rn(cc.z, wc, __fmaf_rn(a.z, wa, __fmul_rn(bb.z, wb)));
+    r.w = __fmaf_rn(cc.w, wc, __fmaf_rn(a.w, wa, __fmul_rn(bb.w, wb)));
+    *reinterpret_cast<float4 *>(o + q * 4) = r;
+  }
+}
+
 // dknown_pm[idx_t][c] += w_t * dout[row][c]; one warp per unknown point, lanes across channels
 __global__ void __launch_bounds__(256)
 fp_interpolate_grad_kernel(int n, int m, int c4n, const float *__restrict__ dout, int ldo,
@@ -576,7 +658,15 @@ PN2_EXPORT int pn2_fp_interpolate(int b, int n, int m, int c, int ld_known, cons
               "pn2_fp_interpolate: bad extents b=%d n=%d m=%d c=%d ld_known=%d ldo=%d", b, n, m, c, ld_known, ldo);
   if (b == 0 || n == 0) return PN2_OK;
   PN2_REQUIRE(unknown && known && known_pm && out && idx && weight && b <= 65535, "pn2_fp_interpolate: null pointer");
-  if (static_cast<long long>(b) * n <= 16384) {
+  static const bool warp_per_point = [] {
+    const char *e = getenv("PN2_FP_WARP");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (static_cast<long long>(b) * n <= 16384 && warp_per_point) {
+    dim3 grid((n + kFpThreads / 32 - 1) / (kFpThreads / 32), b);
+    pn2::launch(fp_interpolate_warp_kernel, dim3(grid), dim3(kFpThreads), 0, static_cast<cudaStream_t>(stream), n, m, c / 4, ld_known, unknown,
+                known, known_pm, out, ldo, idx, weight);
+  } else if (static_cast<long long>(b) * n <= 16384) {
     dim3 grid((n + 31) / 32, b);
     pn2::launch(fp_interpolate_kernel<32>, dim3(grid), dim3(kFpThreads), 0, static_cast<cudaStream_t>(stream), n, m, c / 4, ld_known, unknown,
                                                                                         known, known_pm, out, ldo, idx, weight);
