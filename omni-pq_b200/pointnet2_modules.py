@@ -10,11 +10,13 @@ therefore their `state_dict` keys.
 Two execution paths, both on libpn2_b200.so kernels only:
 
 * fused (`fused.py`): `PointnetSAModuleVotes` with max pooling and `PointnetFPModule` run as a short
-  chain of fused kernels -- FPS (+centre gather), ball query feeding the grouped first MLP layer
-  straight from shared memory, BatchNorm(+ReLU) folded into the next layer's operand load, the last
-  layer reduced to per-group max/min without ever materialising its activations, three_nn +
-  interpolation as one gather-MAC kernel -- with a hand-written backward.  The `nn.Conv2d` /
-  `nn.BatchNorm2d` (or `SyncBatchNorm`) children are only read as parameter holders there.
+  chain of fused kernels -- FPS (+centre gather), ball query (it writes the int32 index tensor, which
+  the backward needs), a first MLP layer that gathers the neighbour rows by index while it stages its
+  operand (the grouped tensor of the reference is never materialised), BatchNorm(+ReLU) folded into
+  the next layer's operand load, BatchNorm + ReLU + max-pool of the last layer as one kernel over its
+  (materialised) pre-activations, three_nn + interpolation as one gather-MAC kernel -- with a
+  hand-written backward.  The `nn.Conv2d` / `nn.BatchNorm2d` (or `SyncBatchNorm`) children are only
+  read as parameter holders there.
 * op-level: every other configuration (MSG variants, avg / rbf pooling, sample_uniformly, GroupAll,
   CPU-less odd shapes) composes the nine op kernels through `pointnet2_utils` exactly like the
   reference does and calls the `SharedMLP` children.
