@@ -291,25 +291,27 @@ int *tile_counter_slot(int dev) {
 // ---- persistent forward / dgrad kernel: async raw ring -> tensor-memory A operand -----------------------------------
 // Round-2 measurements (tools/mma_floor.cu, profiles/r2_mma_floor.txt): twelve kind::tf32 128x128x8 MMAs -- one 32-wide
 // k-block of the 3xTF32 scheme -- take 768 cycles (0.39 us) in SS *and* TS form, with or without concurrent
-// shared-memory store traffic, so the 1.0 / 1.25 us per k-block of gemm_tc_pbulk_kernel is NOT operand bandwidth: it
-// is the producers.  Their global loads were prefetched through registers, and the depth that survives register
+// shared-memory store traffic, so the 1.0 / 1.25 us per k-block of round 1's kernels were NOT operand bandwidth: it
+// was the producers.  Their global loads were prefetched through registers, and the depth that survives register
 // rotation / the 96-register cap is about one k-block, i.e. one memory latency (~1 us) per k-block.
 //
-// Here the loads no longer pass through registers:
+// Here the loads do not pass through registers:
 //   * every producer thread issues its 16-byte pieces of the next k-blocks with cp.async (LDGSTS) into a RAW ring in
 //     shared memory (5 stages of 16 KB for plain / BatchNorm / gather sources, 3 stages of 32-36 KB for the
 //     BatchNorm-backward sources that read y and dz), coalesced (8 lanes = one 128-byte row segment), completion
 //     signalled per stage on an mbarrier (cp.async.mbarrier.arrive.noinc) -- 64-96 KB in flight per SM, independent of
-//     the register allocator; the ring runs ACROSS tile boundaries (tickets are drawn two tiles ahead), so the first
+//     the register allocator; the ring runs ACROSS tile boundaries (tickets are drawn five tiles ahead), so the first
 //     k-blocks of the next tile are in flight during the epilogue of the current one;
 //   * the transform (gather / BN+ReLU / BN backward + pool routing) and the hi/lo split read the raw stage with
 //     thread = tile row (16-byte chunks XOR-swizzled by row: conflict-free) and write the operand straight into TENSOR
 //     MEMORY (tcgen05.st, thread = TMEM lane); the MMAs take A from TMEM (TS form).  The A operand therefore needs no
-//     shared memory at all, which is what pays for the raw ring; 6 A stages live in the 384 TMEM columns next to the
-//     accumulator;
-//   * weights: the pre-split image, one 32 KB bulk copy per k-block, 3-4 stage ring (as before).
-// 16 producer warps + one MMA warp (lane 0 issues) + one weight-loader warp (lane 0 issues the bulk copies, so that
-// waiting for a free weight stage never stalls a producer), one CTA per SM, dynamic tile tickets.
+//     shared memory at all, which is what pays for the raw ring; 6 (128-wide tile) or 4 (256-wide) A stages live in
+//     the tensor-memory columns next to the accumulator;
+//   * weights: the pre-split image in 32 KB slots (128 output rows x one k-block, hi | lo), 3-4 slot ring; a 256-wide
+//     tile consumes two slots per k-block.
+// 16 producer warps + one converged MMA warp (issues under elect.sync) + one weight-loader warp (lane 0 issues the bulk
+// copies, so that waiting for a free weight slot never stalls a producer), one CTA per SM, five static tile tickets,
+// then dynamic ones.
 constexpr int AS_CTA_THREADS = TC_THREADS + 64;
 constexpr uint32_t AS_TMEM_COLS = 512, AS_A_STAGE_COLS = 64;  // accumulator first, then the A stages: 32 hi + 32 lo columns each
 constexpr int AS_ARG_BYTES = TM * TK;                                             // uint8 arg-max slots of a k-block
@@ -561,11 +563,12 @@ gemm_tc_async_kernel(const __grid_constant__ GemmArgs g) {
       }
     }
   } else {
-    // ---- producers.  What a k-block costs here is neither bandwidth nor the tensor pipe but the LENGTH of the per-warp
-    // instruction chain: with 18 warps per SM a warp issues a dependent instruction every ~5 cycles, and this loop
-    // (ring top-up, two barrier waits, shared-memory reads, transform, tcgen05.st + wait, fence + arrive) needs
-    // ~1800 cycles per k-block although a thread only moves 8 values (profiles/r2_tile_trace.txt).  Ring positions and
-    // phase bits are carried incrementally instead of computed.  Rejected variants: TWO k-blocks per iteration (half
+    // ---- producers.  What a k-block costs here is neither bandwidth nor the tensor pipe but INSTRUCTION ISSUE: 16 warps x
+    // ~300 instructions per k-block (ring top-up, three barrier waits, shared-memory reads, transform, split,
+    // tcgen05.st + wait, fence + arrive) over 4 issue slots per cycle is the measured 0.6-0.8 us, although a thread only
+    // moves 8 values (loop bodies counted in the SASS).  Hence: ring positions and phase bits
+    // carried incrementally, row pointers resolved once per tile, shared-window loads with immediates, one try_wait on
+    // the hot path of every barrier, tf32 rounding on the bit pattern.  Rejected variants: TWO k-blocks per iteration (half
     // the barrier round trips per k-block; 63.9 vs 49.1 us on 32768 x 256 -> 256: the MMA warp then receives its stages
     // in bursts) and four warp groups owning every fourth k-block (2.6 us per group and k-block).
     // issue mapping: 16-byte chunk `chunk` of rows rsub, rsub + 64 (8 consecutive lanes = one 128-byte row segment)
@@ -775,8 +778,8 @@ int launch_tc_async(const GemmArgs &g, cudaStream_t stream) {
 // ---- weight-gradient kernel: async raw ring, thread = channel ---------------------------------------------------------
 // dW[cout tile 128][cin tile 128] over a slice of positions (blockIdx.z).  K runs over POSITIONS, and both operands are row
 // sources with the channels contiguous, so the operand tiles are the TRANSPOSE of what arrives from memory.
-// gemm_tc_kernel<TRANS> above does that transposition with MN-major tiles staged through registers, one k-block of
-// prefetch deep: 2.8 us per 32-position k-block where the 48 KB it reads cost ~1 us of the SM's share of HBM.  Here:
+// Round 1's kernel did that transposition with MN-major tiles staged through registers, one k-block of prefetch deep:
+// 2.8 us per 32-position k-block where the 48 KB it reads cost ~1 us of the SM's share of HBM.  Here:
 //   * raw ring (3 stages): per k-block the 32 positions x 128 channels of  y | dz | activation  (+ the pooled arg-max
 //     bytes, + the neighbour / centre coordinates of a gathered source) are copied by cp.async exactly as they lie in
 //     memory -- a warp copies one position's 512 contiguous bytes -- with completion on an mbarrier; two k-blocks
